@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the full-format kinetic update (config C4 of SURVEY.md §8d).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm
+
+Metric (BASELINE.json): cell x v-node updates per second per step.  A "step" is one
+Solver<Full>::_UpdatePDF pass (src/solver.cpp:141-212: upwind face fluxes + E-field
+acceleration + explicit Euler) plus the Density() moment the next step needs, over every tet
+of the rank's mesh block.  Workload at N GPUs: weak scaling, one 28x28x28-hex Kuhn block
+(131,712 tets) x 32^3 velocity nodes per GPU — the per-GPU share of the 1,053,696-tet C4 box.
+
+One JSON line is printed by rank 0.  `value` is timed with the state resident in HBM; `e2e`
+is the same step through the host-buffer C-ABI call (E field in from pinned host memory,
+Density() out) — what one call of the reference-facing Solver exchanges per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# physical set-up of C4 with the reference's constants (src/constants.h:5-12)
+EL_MASS, EL_CHARGE, EPS0, KB, EV = 9.1e-31, 1.6e-19, 8.85e-12, 1.38e-23, 11604.518
+PI = 3.14159265358979323846
+ALGO_BYTES_PER_UPDATE = 16.0     # read f^n once + write f^{n+1} once
+
+
+def c4_setup(hexes, nv):
+    T = 1 * EV
+    dens = 1e17
+    debye = np.sqrt(EPS0 * KB * T / dens) / EL_CHARGE          # particle_data.cpp:155-157
+    wp = EL_CHARGE * np.sqrt(dens / (EL_MASS * EPS0))          # particle_data.cpp:159-162
+    vth = np.sqrt(KB * T / EL_MASS)
+    cell = 50 * debye / 28.0                                   # 28 hexes per 50 Debye lengths
+    lengths = tuple(cell * h for h in hexes)
+    return dict(T=T, dens=dens, lengths=lengths, vmin=[-6 * vth] * 3, vmax=[6 * vth] * 3, n=[nv] * 3,
+                dt=1e-3 * 2 * PI / wp, mass=EL_MASS, charge=-EL_CHARGE)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    smax.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, c[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "k_full_step_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def cpu_baseline(steps=2, warmup=1, hexes=(6, 6, 6), nv=32, threads=None, fused=False):
+    """The oracle's reference-faithful restatement of _UpdatePDF (one temporary per tensor
+    operator, OpenMP over tets as src/solver.cpp:159,187,204) on a bounded sample of C4."""
+    threads = threads or os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    import oracle
+    oracle.build()
+    from vlasovtucker_b200 import synthetic
+    cfg = c4_setup(hexes, nv)
+    nodes, tets, tris, ents = synthetic.kuhn_box(*hexes, cfg["lengths"])
+    m = oracle.Mesh.from_arrays(nodes, tets, tris, ents, [(1, 2), (3, 4), (5, 6)])
+    s = oracle.Sim(m)
+    sp = s.add_species(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
+    x = m.tetCentroid[:, 0] / cfg["lengths"][0]
+    s.set_maxwell(sp, cfg["dens"] * (1 + 0.01 * np.sin(2 * PI * x)), cfg["T"])
+    s.set_params(sp, cfg["dt"], fused=fused)
+    E = np.zeros((m.nTets, 3))
+    E[:, 0] = 1e3 * np.cos(2 * PI * x)
+    for _ in range(warmup):
+        s.update_pdf(sp, E)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        s.update_pdf(sp, E)
+    dt = (time.perf_counter() - t0) / steps
+    updates = m.nTets * nv ** 3
+    return dict(value=updates / dt, unit="updates/s", cores=threads, kind="port",
+                sample=f"Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]}x6={m.nTets} tets x {nv}^3, "
+                       f"{steps} timed _UpdatePDF steps ({'fused single-pass' if fused else 'reference-faithful temporaries'}, "
+                       f"OpenMP {threads} threads)", ms_per_step=dt * 1e3)
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": "cell x v-node updates/s per step (full format)", "value": cb["value"],
+        "unit": "updates/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 1)),
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4 per-GPU share (Kuhn 28^3x6 tets x 32^3 v-nodes, full format); CPU arm timed on a bounded sample",
+                   "note": "reference itself cannot be compiled here (vendored Eigen lacks Eigen/Core); this is the oracle's line-by-line restatement"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    import torch
+    import vlasovtucker_b200 as vtb
+    from vlasovtucker_b200 import synthetic
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    hexes = tuple(args.hexes)
+    nv = args.nv
+    cfg = c4_setup(hexes, nv)
+    if world > 1:
+        from vlasovtucker_b200 import multigpu
+        runner = multigpu.WeakScaledBox(rank, world, local, hexes, cfg, brick=tuple(args.brick), dist=dist)
+        ctx, sp, mt = runner.ctx, runner.sp, runner.mt
+    else:
+        runner = None
+        ctx = vtb.Context(local)
+        mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"], brick=tuple(args.brick))
+        ctx.mesh_upload(mt)
+        sp = ctx.species_create(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
+        ctx.set_face_bc(sp, np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8))
+        x = mt.tetCentroid[:, 0] / cfg["lengths"][0]
+        ctx.set_maxwell(sp, cfg["dens"] * (1 + 0.01 * np.sin(2 * PI * x)), cfg["T"])
+        E = np.zeros((mt.nTets, 3))
+        E[:, 0] = 1e3 * np.cos(2 * PI * x)
+        ctx.field_set(E)
+    ctx.step_config(chunk_planes=args.chunk_planes, variant=args.variant)
+    nT = mt.nTets
+    N = nv ** 3
+    updates_rank = nT * N
+    dt = cfg["dt"]
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        if runner is not None:
+            runner.step(dt)
+        else:
+            ctx.step_full(sp, dt)
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ctx.profile_begin()
+    for _ in range(args.steps):
+        step()
+    region_ms, kern_ms, kern_n = ctx.profile_end()
+    launches = ctx.launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = region_ms
+    if dist is not None:
+        t = torch.tensor([region_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+    ms_per_step = t_ms / args.steps
+    value = updates_rank * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through host buffers (E in from host, Density() out to host)
+    if runner is not None:
+        e2e_ms = runner.e2e(dt, args.steps, barrier)
+    else:
+        Eh = E.copy()
+        dens = np.empty(nT)
+        ctx.step_full_host(sp, dt, Eh, dens)
+        barrier()
+        t0 = time.perf_counter()
+        ctx.profile_begin()
+        for _ in range(args.steps):
+            ctx.step_full_host(sp, dt, Eh, dens)
+        e2e_region_ms, _, _ = ctx.profile_end()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e2e_region_ms, wall_ms)     # host packing is part of the call: take the slower clock
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = updates_rank * world / (e2e_ms / args.steps * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        kern_avg_ms = kern_ms / max(1, kern_n)
+        achieved = ALGO_BYTES_PER_UPDATE * updates_rank / (kern_avg_ms * 1e-3) / 1e9
+        tr = ncu_traffic()
+        line = {
+            "metric": "cell x v-node updates/s per step (full format)", "value": value, "unit": "updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"C4 per-GPU share: periodic Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]} hexes x6 = {nT} tets/GPU "
+                            f"x {nv}^3 velocity nodes, full format, electrons (Maxwellian 1 eV, 1% density wave), dt=1e-3 T_p",
+                "tets_per_gpu": nT, "v_nodes": N, "state_bytes_per_gpu": 2 * nT * N * 8,
+                "l2_policy": "inputs larger than L2 (state is %.1f GB per copy); no flush needed" % (nT * N * 8 / 1e9),
+                "brick_hexes": list(args.brick), "chunk_planes": args.chunk_planes,
+                "step": "K1 full_step (flux+accel+Euler+density partials) + density reduce" + ("; halo push over NVLink" if world > 1 else ""),
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None if tr is None else tr.get("dram_bytes_per_launch"),
+                         "peak_source": peak_src, "kernel": "k_full_step", "kernel_ms": kern_avg_ms,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * updates_rank,
+                         "kernel_share_of_step": kern_ms / region_ms},
+            "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": 3 * nT * 8 * world,
+                    "d2h_bytes_per_step": nT * 8 * world, "ms_per_step": e2e_ms / args.steps,
+                    "what": "vt_step_full_host: E (3 doubles/tet) host->device, step, Density() device->host; state stays resident"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cb = cpu_baseline()
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hexes", type=int, nargs=3, default=[28, 28, 28], help="hexes per GPU block")
+    ap.add_argument("--nv", type=int, default=32)
+    ap.add_argument("--brick", type=int, nargs=3, default=[7, 7, 7], help="L2 brick in hexes")
+    ap.add_argument("--chunk-planes", type=int, default=2)
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+/* vt_b200.h — C ABI of libvt_b200.so, the B200 (sm_100a) implementation of VlasovTucker's
+ * per-time-step kinetic update.
+ *
+ * The reference (DmitriiGurev/VlasovTucker, C++) has no FFI of its own: its boundary for this
+ * path is the header-level C++ API of src/header.h.  The entry points below are what the host
+ * classes of that API (vlasovtucker_b200/host/, same names as the reference's) bind, one per
+ * reference function on the hot path; each comment cites the reference code it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; vt_last_error() gives the text
+ *    (the host classes rethrow it as the std::runtime_error / std::invalid_argument the
+ *    reference would have thrown);
+ *  - all pointers are HOST pointers owned by the caller unless the name ends in _dev;
+ *  - tet-indexed arrays are in the caller's (= reference's) tet order; the library keeps its
+ *    own locality order internally (vt_mesh_upload's `order`) and translates on every call;
+ *  - FP64 throughout; indices are 32-bit; tensors are column-major, i0 fastest, exactly as
+ *    Eigen::Tensor<double,3> in the reference (src/typedefs.h:9);
+ *  - one host thread per context; calls are stream-ordered inside the context;
+ *  - there is no CPU fallback: without a CUDA device vt_ctx_create fails.
+ */
+#ifndef VT_B200_H
+#define VT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vt_ctx vt_ctx;
+
+/* ParticleBCType, src/solver.h:25 */
+enum { VT_PBC_NONBOUNDARY = 0, VT_PBC_PERIODIC = 1, VT_PBC_SOURCE = 2, VT_PBC_ABSORBING = 3, VT_PBC_FREE = 4 };
+/* PoissonBCType, src/poisson.h:47 */
+enum { VT_QBC_NONBOUNDARY = 0, VT_QBC_NEUMANN = 1, VT_QBC_DIRICHLET = 2, VT_QBC_PERIODIC = 3 };
+
+const char* vt_last_error(void);
+int vt_version(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int vt_ctx_create(int device, vt_ctx** out);
+void vt_ctx_destroy(vt_ctx* ctx);
+int vt_sync(vt_ctx* ctx);
+/* device properties the bench reports (SM count, L2 bytes, HBM bytes) */
+int vt_device_info(vt_ctx* ctx, int* sm_count, size_t* l2_bytes, size_t* hbm_bytes);
+
+/* ---- mesh tables: the flattened Mesh the face loop of Solver::_UpdatePDF walks --------------
+ * replaces the Tet / Face pointer-graph reads of src/solver.cpp:163-168, 319 and
+ * src/primitives.h:62-97.
+ *   nOwned        tets this context updates
+ *   nGhost        extra read-only rows appended after the owned ones (multi-GPU halo); a
+ *                 neighbour index in [nOwned, nOwned+nGhost) names a ghost row
+ *   nbr[4*t+j]    tet across face j (tet->adjTets[j]->index), -1 where the reference holds
+ *                 nullptr
+ *   area, volume  face->area (4 per tet), tet->volume
+ *   normal[12*t+3*j+k]   face->normal
+ *   entity[4*t+j] face->entity (-1 internal)
+ *   order         optional permutation: order[p] = caller index of the tet stored at device
+ *                 row p (NULL = identity).  Pure layout hint; results do not depend on it.
+ */
+int vt_mesh_upload(vt_ctx* ctx, int nOwned, int nGhost, const int32_t* nbr, const double* area,
+                   const double* volume, const double* normal, const int32_t* entity,
+                   const int32_t* order);
+
+/* ---- species: VelocityGrid + ParticleData<Full> + the per-face particle BCs of Solver -------
+ * replaces VelocityGrid (src/velocity_grid.cpp:9-53) and ParticleData (src/particle_data.h:21-52).
+ */
+int vt_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], const double vmax[3],
+                      double mass, double charge, int* species);
+/* Solver::SetParticleBC (src/solver.cpp:62-71): per-face BC type (uint8, 4 per tet), the
+ * collectCharge flag, and for Source faces an index into the source-PDF table (-1 otherwise). */
+int vt_species_set_face_bc(vt_ctx* ctx, int species, const uint8_t* bcType, const uint8_t* collect,
+                           const int32_t* sourceId);
+/* ParticleBC::sourcePDF tensors (src/solver.h:31), nSource x N doubles */
+int vt_species_set_source_pdfs(vt_ctx* ctx, int species, int nSource, const double* pdf);
+/* pdf[t] = Full(tensor) for t in [first, first+count): caller order, N doubles per tet */
+int vt_species_set_pdf(vt_ctx* ctx, int species, int first, int count, const double* pdf);
+/* pdf[t].Reconstructed() (src/full.cpp:24-27) */
+int vt_species_get_pdf(vt_ctx* ctx, int species, int first, int count, double* pdf);
+/* SetMaxwellPDF on the device (src/particle_data.cpp:23-90) */
+int vt_species_set_maxwell(vt_ctx* ctx, int species, const double* physDensity, double temperature,
+                           const double mostProbableV[3]);
+/* ParticleData::Density (src/particle_data.cpp:93-102) and Velocity (:105-125);
+ * out may be NULL (result stays on the device for the Poisson step) */
+int vt_species_density(vt_ctx* ctx, int species, double* density);
+int vt_species_velocity(vt_ctx* ctx, int species, double* velocity /* 3 per tet */);
+
+/* ---- field ---------------------------------------------------------------------------------- */
+/* copy a caller-computed field (3 doubles per tet) to the device; replaces Solver::_field
+ * (src/solver.cpp:110) when the Poisson solve ran elsewhere */
+int vt_field_set(vt_ctx* ctx, const double* E);
+int vt_field_get(vt_ctx* ctx, double* rho, double* phi, double* E);
+
+/* ---- the hot path: Solver<Full>::_UpdatePDF (src/solver.cpp:141-212) ------------------------
+ * rhs = -sum_f (A_f/V) flux_f - sum_k (q/m)(E_k+ext_k) d f/d v_k ;  f += dt*rhs, for every owned
+ * tet, using the field currently on the device.  Also leaves Density() of the new state on the
+ * device and accumulates the absorbed wall charge (src/solver.cpp:171-178). */
+int vt_step_full(vt_ctx* ctx, int species, double dt, const double ext[3]);
+/* the same through host buffers, as one call of the reference-facing Solver would do it: copies
+ * E (3*nOwned doubles) host->device, steps, copies Density() (nOwned doubles) device->host */
+int vt_step_full_host(vt_ctx* ctx, int species, double dt, const double ext[3], const double* E,
+                      double* density);
+/* tuning knobs of the step kernel: planes of the velocity grid per CTA (0 = whole tensor) and
+ * tets per L2 brick (0 = default) */
+int vt_step_config(vt_ctx* ctx, int chunkPlanes, int brickTets, int variant);
+/* device time of the last vt_step_full kernel in milliseconds (CUDA events) and launches so far */
+int vt_step_last_ms(vt_ctx* ctx, float* ms);
+long vt_launch_count(vt_ctx* ctx);
+/* measurement on the context's own stream (CUDA events): vt_profile_begin marks the start of a
+ * timed region; vt_profile_end synchronises and returns the region's device time, the summed
+ * device time of the step kernels launched inside it and how many there were */
+int vt_profile_begin(vt_ctx* ctx);
+int vt_profile_end(vt_ctx* ctx, float* region_ms, float* step_kernel_ms, int* step_kernels);
+
+/* wall charge, src/solver.cpp:171-178, 296-311: accumulated charge of entity */
+int vt_wall_charge_get(vt_ctx* ctx, int species, int entity, double* charge);
+int vt_wall_charge_reset(vt_ctx* ctx, int species);
+
+/* ---- Poisson: PoissonSolver (src/poisson.cpp) ----------------------------------------------- */
+/* geometry the field kernels need beyond vt_mesh_upload: centroids (3 per tet) and face
+ * centroids (12 per tet), plus per-face BC (type uint8, value, normalGrad)
+ * — PoissonSolver::SetBC / Initialize (src/poisson.cpp:85-124) */
+int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceCentroid,
+                     const uint8_t* bcType, const double* bcValue, const double* bcNormalGrad);
+/* Neumann/Dirichlet data may change between solves (src/solver.cpp:120-132) */
+int vt_poisson_update_bc_values(vt_ctx* ctx, const double* bcValue, const double* bcNormalGrad);
+/* PoissonSolver::Solve (src/poisson.cpp:179-213); rho NULL = use the device-resident charge
+ * density assembled by vt_charge_density.  phi/E may be NULL. */
+int vt_poisson_solve(vt_ctx* ctx, const double* rho, double* phi, double* E);
+int vt_poisson_stats(vt_ctx* ctx, int* lastIterations, double* lastRelResidual);
+/* rho = sum_s charge_s * Density_s + background (src/solver.cpp:98-105,
+ * src/multicomponent_solver.cpp:61-74); background may be NULL */
+int vt_charge_density(vt_ctx* ctx, const int* species, int nSpecies, const double* background);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VT_B200_H */

@@ -1,0 +1,220 @@
+"""Thin Python mirror of the C ABI (include/vt_b200.h) used by tests and bench.py.
+
+The names follow the reference's domain: a context owns the flattened ``Mesh`` tables, each
+species owns a ``VelocityGrid`` + ``ParticleData<Full>`` state on the device, ``step_full`` is
+``Solver<Full>::_UpdatePDF`` (src/solver.cpp:141-212).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+PBC = dict(NonBoundary=0, Periodic=1, Source=2, Absorbing=3, Free=4)   # src/solver.h:25
+QBC = dict(NonBoundary=0, Neumann=1, Dirichlet=2, Periodic=3)           # src/poisson.h:47
+
+
+@dataclass
+class MeshTables:
+    """Flattened ``Mesh`` after ``Reconstruct`` (src/mesh.cpp:94-111), reference tet order."""
+    nbr: np.ndarray            # (nT,4) int32, -1 where the reference holds nullptr
+    area: np.ndarray           # (nT,4)
+    volume: np.ndarray         # (nT,)
+    normal: np.ndarray         # (nT,4,3)
+    entity: np.ndarray         # (nT,4) int32, -1 internal
+    tetCentroid: np.ndarray    # (nT,3)
+    faceCentroid: np.ndarray   # (nT,4,3)
+    order: np.ndarray = None   # locality permutation for the device layout (optional)
+    brickTets: int = 0         # tets per L2 brick matching `order` (0 = library default)
+    nGhost: int = 0
+    periodic: list = field(default_factory=list)
+
+    @property
+    def nTets(self):
+        return len(self.volume)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        capi.check(self.lib.vt_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.nOwned = 0
+        self.grids = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vt_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_info(self):
+        sm = C.c_int()
+        l2 = C.c_size_t()
+        hbm = C.c_size_t()
+        capi.check(self.lib.vt_device_info(self.h, C.byref(sm), C.byref(l2), C.byref(hbm)))
+        return dict(sm_count=sm.value, l2_bytes=l2.value, hbm_bytes=hbm.value)
+
+    def sync(self):
+        capi.check(self.lib.vt_sync(self.h))
+
+    # ---- mesh
+    def mesh_upload(self, mt: MeshTables):
+        nbr = capi.i32(mt.nbr)
+        area = capi.f64(mt.area)
+        vol = capi.f64(mt.volume)
+        nrm = capi.f64(mt.normal)
+        ent = capi.i32(mt.entity)
+        order = capi.i32(mt.order)
+        self.nOwned = len(vol)
+        self.mesh = mt
+        capi.check(self.lib.vt_mesh_upload(self.h, self.nOwned, int(mt.nGhost), capi.ip(nbr), capi.dp(area),
+                                           capi.dp(vol), capi.dp(nrm), capi.ip(ent), capi.ip(order)))
+        if mt.brickTets:
+            self.step_config(brick_tets=mt.brickTets)
+
+    # ---- species
+    def species_create(self, n, vmin, vmax, mass, charge):
+        n = capi.i32(n)
+        vmin = capi.f64(vmin)
+        vmax = capi.f64(vmax)
+        sp = C.c_int()
+        capi.check(self.lib.vt_species_create(self.h, capi.ip(n), capi.dp(vmin), capi.dp(vmax), float(mass),
+                                              float(charge), C.byref(sp)))
+        self.grids.append(tuple(int(x) for x in n))
+        return sp.value
+
+    def N(self, sp):
+        n = self.grids[sp]
+        return n[0] * n[1] * n[2]
+
+    def set_face_bc(self, sp, bc_type, collect=None, source_id=None):
+        bc = capi.u8(bc_type)
+        col = capi.u8(collect)
+        src = capi.i32(source_id)
+        capi.check(self.lib.vt_species_set_face_bc(self.h, sp, capi.u8p(bc), capi.u8p(col), capi.ip(src)))
+
+    def set_source_pdfs(self, sp, pdfs):
+        pdfs = capi.f64(pdfs).reshape(-1, self.N(sp))
+        capi.check(self.lib.vt_species_set_source_pdfs(self.h, sp, len(pdfs), capi.dp(pdfs)))
+
+    def set_pdf(self, sp, f, first=0):
+        f = capi.f64(f).reshape(-1, self.N(sp))
+        capi.check(self.lib.vt_species_set_pdf(self.h, sp, int(first), len(f), capi.dp(f)))
+
+    def get_pdf(self, sp, first=0, count=None):
+        count = self.nOwned - first if count is None else count
+        out = np.empty((count, self.N(sp)))
+        capi.check(self.lib.vt_species_get_pdf(self.h, sp, int(first), int(count), capi.dp(out)))
+        return out
+
+    def set_maxwell(self, sp, density, temperature, mpv=(0.0, 0.0, 0.0)):
+        d = capi.f64(density)
+        v = capi.f64(mpv)
+        capi.check(self.lib.vt_species_set_maxwell(self.h, sp, capi.dp(d), float(temperature), capi.dp(v)))
+
+    def density(self, sp, download=True):
+        out = np.empty(self.nOwned) if download else None
+        capi.check(self.lib.vt_species_density(self.h, sp, capi.dp(out)))
+        return out
+
+    def velocity(self, sp):
+        out = np.empty((self.nOwned, 3))
+        capi.check(self.lib.vt_species_velocity(self.h, sp, capi.dp(out)))
+        return out
+
+    # ---- field
+    def field_set(self, E):
+        E = capi.f64(E)
+        capi.check(self.lib.vt_field_set(self.h, capi.dp(E)))
+
+    def field_get(self):
+        rho, phi, E = np.empty(self.nOwned), np.empty(self.nOwned), np.empty((self.nOwned, 3))
+        capi.check(self.lib.vt_field_get(self.h, capi.dp(rho), capi.dp(phi), capi.dp(E)))
+        return rho, phi, E
+
+    # ---- hot path
+    def step_full(self, sp, dt, ext=(0.0, 0.0, 0.0)):
+        ext = capi.f64(ext)
+        capi.check(self.lib.vt_step_full(self.h, sp, float(dt), capi.dp(ext)))
+
+    def step_full_host(self, sp, dt, E, density_out, ext=(0.0, 0.0, 0.0)):
+        ext = capi.f64(ext)
+        assert E.dtype == np.float64 and E.flags.c_contiguous and density_out.flags.c_contiguous
+        capi.check(self.lib.vt_step_full_host(self.h, sp, float(dt), capi.dp(ext), capi.dp(E), capi.dp(density_out)))
+
+    def step_config(self, chunk_planes=None, brick_tets=None, variant=None):
+        self._cfg = getattr(self, "_cfg", [0, 0, 0])
+        if chunk_planes is not None:
+            self._cfg[0] = int(chunk_planes)
+        if brick_tets is not None:
+            self._cfg[1] = int(brick_tets)
+        if variant is not None:
+            self._cfg[2] = int(variant)
+        capi.check(self.lib.vt_step_config(self.h, *self._cfg))
+
+    def step_last_ms(self):
+        ms = C.c_float()
+        capi.check(self.lib.vt_step_last_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.vt_launch_count(self.h))
+
+    def profile_begin(self):
+        capi.check(self.lib.vt_profile_begin(self.h))
+
+    def profile_end(self):
+        """(region_ms, step_kernel_ms, step_kernels) measured with CUDA events on the context stream."""
+        r, k, n = C.c_float(), C.c_float(), C.c_int()
+        capi.check(self.lib.vt_profile_end(self.h, C.byref(r), C.byref(k), C.byref(n)))
+        return r.value, k.value, n.value
+
+    def wall_charge(self, sp, entity):
+        q = C.c_double()
+        capi.check(self.lib.vt_wall_charge_get(self.h, sp, int(entity), C.byref(q)))
+        return q.value
+
+    def wall_charge_reset(self, sp):
+        capi.check(self.lib.vt_wall_charge_reset(self.h, sp))
+
+    # ---- Poisson
+    def poisson_setup(self, bc_type, bc_value=None, bc_normal_grad=None):
+        mt = self.mesh
+        nT = self.nOwned
+        bc = capi.u8(bc_type).reshape(nT, 4)
+        val = capi.f64(np.zeros((nT, 4)) if bc_value is None else bc_value)
+        ng = capi.f64(np.zeros((nT, 4)) if bc_normal_grad is None else bc_normal_grad)
+        tc = capi.f64(mt.tetCentroid)
+        fc = capi.f64(mt.faceCentroid)
+        capi.check(self.lib.vt_poisson_setup(self.h, capi.dp(tc), capi.dp(fc), capi.u8p(bc), capi.dp(val), capi.dp(ng)))
+
+    def poisson_update_bc_values(self, bc_value, bc_normal_grad):
+        val = capi.f64(bc_value)
+        ng = capi.f64(bc_normal_grad)
+        capi.check(self.lib.vt_poisson_update_bc_values(self.h, capi.dp(val), capi.dp(ng)))
+
+    def poisson_solve(self, rho=None, download=True):
+        rho = capi.f64(rho)
+        phi = np.empty(self.nOwned) if download else None
+        E = np.empty((self.nOwned, 3)) if download else None
+        capi.check(self.lib.vt_poisson_solve(self.h, capi.dp(rho), capi.dp(phi), capi.dp(E)))
+        return phi, E
+
+    def poisson_stats(self):
+        it = C.c_int()
+        res = C.c_double()
+        capi.check(self.lib.vt_poisson_stats(self.h, C.byref(it), C.byref(res)))
+        return it.value, res.value
+
+    def charge_density(self, species, background=None):
+        sp = capi.i32(species)
+        bg = capi.f64(background)
+        capi.check(self.lib.vt_charge_density(self.h, capi.ip(sp), len(sp), capi.dp(bg)))

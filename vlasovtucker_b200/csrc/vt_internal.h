@@ -1,0 +1,122 @@
+// Internal structures of libvt_b200 (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vt_b200.h"
+
+#define VT_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_));    \
+    } while (0)
+
+namespace vt {
+
+// One record per owned tet, device order.  Read once per CTA into shared memory.
+struct TetRec {
+    double coef[4];      // face->area / tet->volume            (solver.cpp:168)
+    double nrm[4][3];    // face->normal                        (solver.cpp:271)
+    int32_t nbr[4];      // device row of tet->adjTets[f]; -1 none; <= -2: source PDF -2-id
+    uint8_t bc[4];       // ParticleBCType                      (solver.h:25)
+    int8_t wallSlot[4];  // >= 0: Absorbing && collectCharge -> accumulator slot (solver.cpp:171)
+    double area[4];      // face->area (wall charge)            (solver.cpp:173)
+};
+
+struct StepParams {
+    const double* f;      // state at step n, rows of N doubles (owned then ghost)
+    double* fn;           // state at step n+1
+    const TetRec* rec;
+    const double* E;      // 3 per owned tet, device order
+    const double* src;    // source PDFs, rows of N doubles
+    double* densPartial;  // [nOwned * nChunks] sum over the chunk of f^{n+1}
+    double* wall;         // [nSlots] absorbed charge accumulators
+    int nOwned;
+    int n0, n1, n2, N;
+    int nvec0;            // n0 / VEC
+    int nLG;              // line groups per CTA = blockDim / nvec0
+    int chunkPlanes, nChunks, brickTets;
+    double vmin[3], step[3], inv2h[3];
+    double qm;            // charge / mass
+    double ext[3];
+    double dt;
+    double wallScale;     // charge * dt * cellVolume
+};
+
+struct Species {
+    int n[3];
+    int N;
+    double vmin[3], vmax[3], step[3], cellVolume;
+    double mass, charge;
+    double* f[2] = {nullptr, nullptr};
+    int cur = 0;
+    TetRec* rec = nullptr;            // device, per owned tet (BCs folded in)
+    std::vector<TetRec> recHost;
+    double* src = nullptr;
+    int nSrc = 0;
+    double* density = nullptr;        // device, owned tets, device order
+    double* densPartial = nullptr;
+    int densPartialCap = 0;
+    bool densityValid = false;
+    double* wall = nullptr;           // device accumulators
+    std::vector<int> wallEntities;    // slot -> entity
+    std::vector<uint8_t> bcType, collect;
+    std::vector<int32_t> sourceId;
+    int danglingFaces = 0;            // boundary faces with neither neighbour nor particle BC
+};
+
+struct PoissonData;
+
+}  // namespace vt
+
+struct vt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop;
+    long launches = 0;
+    float lastStepMs = 0;
+    // profiling region (vt_profile_begin/end): one event pair per step-kernel launch
+    bool profiling = false;
+    cudaEvent_t regionStart = nullptr, regionStop = nullptr;
+    std::vector<cudaEvent_t> kernelEvents;   // pairs, grown on demand and reused
+    size_t kernelEventsUsed = 0;
+
+    int nOwned = 0, nGhost = 0;
+    std::vector<int32_t> order, inv;   // order[p] = caller tet at device row p; inv = inverse
+    bool identityOrder = true;
+    std::vector<int32_t> nbrHost;      // device-order, device-row neighbour indices
+    std::vector<double> area, volume, normal;   // caller order
+    std::vector<int32_t> entity;                // caller order
+    int32_t* orderDev = nullptr;
+    int32_t* invDev = nullptr;
+
+    std::vector<vt::Species*> species;
+
+    double* E = nullptr;       // device, 3 per owned tet, device order
+    double* rho = nullptr;     // device order
+    double* phi = nullptr;
+    double* stage = nullptr;   // staging buffer for permuted host<->device copies
+    size_t stageBytes = 0;
+    double* pinned = nullptr;  // pinned host staging
+    size_t pinnedBytes = 0;
+
+    int chunkPlanes = 0, brickTets = 0, variant = 0;
+
+    vt::PoissonData* poisson = nullptr;
+};
+
+namespace vt {
+void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3]);
+void launch_density(vt_ctx* ctx, Species& sp);
+void poisson_destroy(PoissonData* p);
+double* ctx_stage(vt_ctx* ctx, size_t bytes);
+double* ctx_pinned(vt_ctx* ctx, size_t bytes);
+}  // namespace vt
