@@ -113,6 +113,25 @@ long vt_launch_count(vt_ctx* ctx);
 int vt_profile_begin(vt_ctx* ctx);
 int vt_profile_end(vt_ctx* ctx, float* region_ms, float* step_kernel_ms, int* step_kernels);
 
+/* ---- multi-GPU halo (one process per GPU; the reference is single-process, so this has no
+ * reference counterpart: it is what keeps Solver::_UpdatePDF's neighbour reads, src/solver.cpp:
+ * 319-327, valid when the mesh is partitioned).  Ghost rows live after the owned rows of each
+ * species' state buffers.  The step kernel itself writes every boundary tet's new state into
+ * the ghost rows of the peer GPUs (NVLink peer stores through CUDA-IPC mappings), so the
+ * exchange is fused with the sweep; vt_halo_barrier is the only synchronisation between steps.
+ *   vt_halo_export   3 x 64-byte CUDA IPC handles: state buffer 0, state buffer 1, barrier flags
+ *   vt_halo_attach   open the peers' handles (peerHandles = nPeers x 192 bytes, same layout)
+ *   vt_halo_set_push for each owned tet (caller order) up to 4 (peer index, ghost row on that
+ *                    peer) pairs, -1 = unused
+ *   vt_halo_push_current  copy the current state of the pushed tets to the peers (initial fill)
+ *   vt_halo_barrier  device-side barrier with all attached peers on the context stream */
+int vt_halo_export(vt_ctx* ctx, int species, void* handles);
+int vt_halo_attach(vt_ctx* ctx, int species, int myRank, int nPeers, const int32_t* peerRanks,
+                   const void* peerHandles);
+int vt_halo_set_push(vt_ctx* ctx, int species, const int32_t* pushPeer, const int32_t* pushRow);
+int vt_halo_push_current(vt_ctx* ctx, int species);
+int vt_halo_barrier(vt_ctx* ctx);
+
 /* wall charge, src/solver.cpp:171-178, 296-311: accumulated charge of entity */
 int vt_wall_charge_get(vt_ctx* ctx, int species, int entity, double* charge);
 int vt_wall_charge_reset(vt_ctx* ctx, int species);

@@ -51,6 +51,24 @@ def face_bc_arrays(m, spec):
     return bc, col
 
 
+def poisson_bc_arrays(m, spec):
+    """Per-face field-BC arrays from {entity: (kind, value, normalGrad)} as PoissonSolver::SetBC
+    (src/poisson.cpp:85-92) would assign them; periodic pairs of the mesh get Periodic."""
+    from vlasovtucker_b200 import QBC
+    bc = np.zeros((m.nTets, 4), np.uint8)
+    val = np.zeros((m.nTets, 4))
+    ng = np.zeros((m.nTets, 4))
+    for pair in getattr(m, "periodic", []):
+        for e in pair:
+            bc[m.faceEntity == e] = QBC["Periodic"]
+    for e, (kind, value, grad) in spec.items():
+        sel = m.faceEntity == e
+        bc[sel] = QBC[kind]
+        val[sel] = value
+        ng[sel] = grad
+    return bc, val, ng
+
+
 @pytest.fixture(scope="session")
 def oracle_mod():
     import oracle

@@ -1,0 +1,26 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the partitioned update with
+the halo exchange fused into the step kernel reproduces the single-GPU update bit for bit."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("variant", ["0", "2"])
+def test_partitioned_update_bit_identical(variant):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if n >= 4 else 2
+    env = dict(os.environ, VT_VARIANT=variant)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "mgpu_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MGPU_CHECK_OK" in r.stdout

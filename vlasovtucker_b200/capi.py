@@ -42,6 +42,11 @@ SIGNATURES = {
     "vt_launch_count": (C.c_long, [C.c_void_p]),
     "vt_profile_begin": (C.c_int, [C.c_void_p]),
     "vt_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "vt_halo_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vt_halo_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_ip, C.c_void_p]),
+    "vt_halo_set_push": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_ip]),
+    "vt_halo_push_current": (C.c_int, [C.c_void_p, C.c_int]),
+    "vt_halo_barrier": (C.c_int, [C.c_void_p]),
     "vt_wall_charge_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp]),
     "vt_wall_charge_reset": (C.c_int, [C.c_void_p, C.c_int]),
     "vt_poisson_setup": (C.c_int, [C.c_void_p, c_dp, c_dp, c_u8p, c_dp, c_dp]),

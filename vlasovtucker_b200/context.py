@@ -185,6 +185,30 @@ class Context:
     def wall_charge_reset(self, sp):
         capi.check(self.lib.vt_wall_charge_reset(self.h, sp))
 
+    # ---- multi-GPU halo
+    HALO_HANDLE_BYTES = 192
+
+    def halo_export(self, sp):
+        buf = np.zeros(self.HALO_HANDLE_BYTES, np.uint8)
+        capi.check(self.lib.vt_halo_export(self.h, sp, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    def halo_attach(self, sp, my_rank, peer_ranks, peer_handles):
+        pr = capi.i32(peer_ranks)
+        ph = np.ascontiguousarray(peer_handles, np.uint8).reshape(len(pr), self.HALO_HANDLE_BYTES)
+        capi.check(self.lib.vt_halo_attach(self.h, sp, int(my_rank), len(pr), capi.ip(pr), ph.ctypes.data_as(C.c_void_p)))
+
+    def halo_set_push(self, sp, push_peer, push_row):
+        pp = capi.i32(push_peer).reshape(self.nOwned, 4)
+        pr = capi.i32(push_row).reshape(self.nOwned, 4)
+        capi.check(self.lib.vt_halo_set_push(self.h, sp, capi.ip(pp), capi.ip(pr)))
+
+    def halo_push_current(self, sp):
+        capi.check(self.lib.vt_halo_push_current(self.h, sp))
+
+    def halo_barrier(self):
+        capi.check(self.lib.vt_halo_barrier(self.h))
+
     # ---- Poisson
     def poisson_setup(self, bc_type, bc_value=None, bc_normal_grad=None):
         mt = self.mesh

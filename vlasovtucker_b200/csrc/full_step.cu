@@ -15,6 +15,12 @@
 // Inside a CTA a thread owns one i0-vector (VEC doubles) and walks lines (i1,i2); the
 // face-normal velocity v.n is split into a per-thread part n_x*v0(i0) kept in registers and a
 // per-line part n_y*v1(i1)+n_z*v2(i2) tabulated once per CTA in shared memory.
+//
+// Two arithmetic variants of the interior face flux (vt_step_config's `variant`, bit 1):
+//   reference shape   0.5*(vn*(fa+f) - |vn|*(fa-f))                       (solver.cpp:325-327)
+//   upwind select     vn>0 ? vn*f : vn*fa, with A_f/V folded into vn: the same first-order
+//                     upwind flux in 2 FP64 operations per face instead of 6; differs from the
+//                     reference expression by rounding only (the parity tests run both).
 #include "vt_internal.h"
 
 namespace vt {
@@ -22,62 +28,42 @@ namespace vt {
 namespace {
 
 template <int VEC>
-struct Vec;
-template <>
-struct Vec<1> {
-    double x;
-};
-template <>
-struct Vec<2> {
-    double x, y;
+struct Vec {
+    double v[VEC];
 };
 
 template <int VEC>
-__device__ __forceinline__ Vec<VEC> ldv(const double* p);
-template <>
-__device__ __forceinline__ Vec<1> ldv<1>(const double* p)
+__device__ __forceinline__ Vec<VEC> ldv(const double* p)
 {
-    Vec<1> r;
-    r.x = __ldg(p);
+    Vec<VEC> r;
+    if (VEC == 2) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+        r.v[0] = t.x;
+        r.v[VEC - 1] = t.y;
+    } else {
+        r.v[0] = __ldg(p);
+    }
     return r;
 }
-template <>
-__device__ __forceinline__ Vec<2> ldv<2>(const double* p)
-{
-    double2 t = __ldg(reinterpret_cast<const double2*>(p));
-    Vec<2> r;
-    r.x = t.x;
-    r.y = t.y;
-    return r;
-}
-// neighbour rows are streamed: read-only path, do not pollute L1
+// neighbour rows are streamed once per CTA: read-only path, do not pollute L1
 template <int VEC>
-__device__ __forceinline__ Vec<VEC> ldv_stream(const double* p);
-template <>
-__device__ __forceinline__ Vec<1> ldv_stream<1>(const double* p)
+__device__ __forceinline__ Vec<VEC> ldv_stream(const double* p)
 {
-    Vec<1> r;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r.x) : "l"(p));
-    return r;
-}
-template <>
-__device__ __forceinline__ Vec<2> ldv_stream<2>(const double* p)
-{
-    Vec<2> r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    Vec<VEC> r;
+    if (VEC == 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                     : "=d"(r.v[0]), "=d"(r.v[VEC - 1])
+                     : "l"(p));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r.v[0]) : "l"(p));
+    }
     return r;
 }
 template <int VEC>
-__device__ __forceinline__ void stv(double* p, const Vec<VEC>& v);
-template <>
-__device__ __forceinline__ void stv<1>(double* p, const Vec<1>& v)
+__device__ __forceinline__ void stv(double* p, const Vec<VEC>& x)
 {
-    *p = v.x;
-}
-template <>
-__device__ __forceinline__ void stv<2>(double* p, const Vec<2>& v)
-{
-    *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y);
+    if (VEC == 2) *reinterpret_cast<double2*>(p) = make_double2(x.v[0], x.v[VEC - 1]);
+    else *p = x.v[0];
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -87,19 +73,147 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// One face's contribution for one element, keeping the reference's expression shape
-// 0.5*(vn*(fa+f) - |vn|*(fa-f)) (solver.cpp:325-327) so differences stay at FMA level.
-__device__ __forceinline__ double flux_pair(double vn, double fa, double f)
+__device__ __forceinline__ bool is_pair(int bc)
 {
-    return 0.5 * (vn * (fa + f) - fabs(vn) * (fa - f));
-}
-__device__ __forceinline__ double flux_absorb(double vn, double f)
-{
-    return 0.5 * (vn * f + fabs(vn) * f);  // solver.cpp:331-332
+    return bc == VT_PBC_NONBOUNDARY || bc == VT_PBC_PERIODIC || bc == VT_PBC_SOURCE;
 }
 
-template <int VEC, bool SHFL>
-__global__ void __launch_bounds__(256) k_full_step(const StepParams p)
+// The per-line loop of one CTA.  GENERIC: per-face boundary-condition dispatch (CTA-uniform
+// branches); otherwise all four faces are interior/periodic/source pairs.
+template <int VEC, bool SHFL, bool GENERIC, bool UPWIND, bool HALO>
+__device__ __forceinline__ void line_loop(const StepParams& p, const TetRec& rec, const int tet, const int c0,
+                                          const int lg, const int pl0, const int nLines,
+                                          const double* __restrict__ v0, const double* __restrict__ bl,
+                                          double& accDens, double (&accWall)[4])
+{
+    const int n0 = p.n0, n1 = p.n1, n2 = p.n2;
+    const int i0 = c0 * VEC;
+    double a[4][VEC], hc[4];
+    bool pair[4], absorbing[4], collect[4];
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+        const int bc = GENERIC ? rec.bc[f] : VT_PBC_NONBOUNDARY;
+        pair[f] = is_pair(bc);
+        absorbing[f] = GENERIC && bc == VT_PBC_ABSORBING;
+        collect[f] = GENERIC && rec.wallSlot[f] >= 0;
+        const bool pre = UPWIND && pair[f];
+        // reference shape: rhs -= coef*(0.5*t) == rhs - (0.5*coef)*t (the halving is exact)
+        hc[f] = pair[f] ? 0.5 * rec.coef[f] : rec.coef[f];
+#pragma unroll
+        for (int u = 0; u < VEC; u++) a[f][u] = (pre ? rec.coef[f] : 1.0) * (rec.nrm[f][0] * v0[i0 + u]);
+    }
+    const double* frow = p.f + (size_t)tet * p.N;
+    double* nrow = p.fn + (size_t)tet * p.N;
+    const double* nbp[4];
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+        const int n = rec.nbr[f];
+        nbp[f] = n >= 0 ? p.f + (size_t)n * p.N : (n <= -2 ? p.src + (size_t)(-2 - n) * p.N : frow);
+    }
+    double* push[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (HALO) {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (rec.pushPeer[q] >= 0) push[q] = p.peerFn[rec.pushPeer[q]] + (size_t)rec.pushRow[q] * p.N;
+    }
+    // force_k / (2 step_k) with force = (q/m)*(E_k+ext_k) as solver.cpp:193-194
+    double g[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) g[k] = (p.qm * (p.E[3 * (size_t)tet + k] + p.ext[k])) * p.inv2h[k];
+
+    const int plane = n0 * n1;
+    // periodic wrap in velocity space (solver.cpp:380-389)
+    const int offL = (i0 == 0) ? (n0 - 1) : -1;                         // left of the first element
+    const int offR = (VEC - 1) + ((i0 + VEC == n0) ? -(n0 - 1) : 1);    // right of the last element
+
+    int l = lg;
+    int i1 = l % n1, pl = l / n1;
+    const int dI1 = p.nLG % n1, dPl = p.nLG / n1;
+    int e = (pl0 * n1 + l) * n0 + i0;
+    const int de = p.nLG * n0;
+
+    for (; l < nLines; l += p.nLG) {
+        const int i2 = pl0 + pl;
+        const Vec<VEC> fc = ldv<VEC>(frow + e);
+        Vec<VEC> fa[4];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            if (!GENERIC || pair[f]) fa[f] = ldv_stream<VEC>(nbp[f] + e);
+            else
+#pragma unroll
+                for (int u = 0; u < VEC; u++) fa[f].v[u] = 0.0;
+        }
+        const int e1m = e + ((i1 == 0) ? (n1 - 1) : -1) * n0;
+        const int e1p = e + ((i1 == n1 - 1) ? -(n1 - 1) : 1) * n0;
+        const int e2m = e + ((i2 == 0) ? (n2 - 1) : -1) * plane;
+        const int e2p = e + ((i2 == n2 - 1) ? -(n2 - 1) : 1) * plane;
+        const Vec<VEC> f1m = ldv<VEC>(frow + e1m), f1p = ldv<VEC>(frow + e1p);
+        const Vec<VEC> f2m = ldv<VEC>(frow + e2m), f2p = ldv<VEC>(frow + e2p);
+        double fl, fr;   // left of the first element, right of the last
+        if (SHFL) {
+            fl = __shfl_sync(0xffffffffu, fc.v[VEC - 1], (c0 + p.nvec0 - 1) & (p.nvec0 - 1), p.nvec0);
+            fr = __shfl_sync(0xffffffffu, fc.v[0], (c0 + 1) & (p.nvec0 - 1), p.nvec0);
+        } else {
+            fl = __ldg(frow + e + offL);
+            fr = __ldg(frow + e + offR);
+        }
+        double blf[4];
+#pragma unroll
+        for (int f = 0; f < 4; f++) blf[f] = bl[4 * l + f];
+
+        Vec<VEC> out;
+#pragma unroll
+        for (int u = 0; u < VEC; u++) {
+            const double fv = fc.v[u];
+            double rhs = 0.0;
+#pragma unroll
+            for (int f = 0; f < 4; f++) {
+                const double vn = a[f][u] + blf[f];
+                if (!GENERIC || pair[f]) {
+                    if (UPWIND) {
+                        // vn here is (A/V)*v.n; upwind value: own cell for outflow, neighbour for inflow
+                        rhs = fma(-vn, vn > 0.0 ? fv : fa[f].v[u], rhs);
+                    } else {
+                        const double s = fa[f].v[u] + fv, d = fa[f].v[u] - fv;
+                        rhs = fma(-hc[f], fma(vn, s, -(fabs(vn) * d)), rhs);   // solver.cpp:325-327, :168
+                    }
+                } else if (absorbing[f]) {
+                    const double flux = 0.5 * (vn * fv + fabs(vn) * fv);      // solver.cpp:331-332
+                    if (collect[f]) accWall[f] += flux;
+                    rhs = fma(-hc[f], flux, rhs);
+                } else {
+                    rhs = fma(-hc[f], vn * fv, rhs);                          // Free, solver.cpp:342
+                }
+            }
+            const double xm = (u == 0) ? fl : fc.v[u - 1 >= 0 ? u - 1 : 0];
+            const double xp = (u == VEC - 1) ? fr : fc.v[u + 1 < VEC ? u + 1 : VEC - 1];
+            rhs = fma(-g[0], xp - xm, rhs);
+            rhs = fma(-g[1], f1p.v[u] - f1m.v[u], rhs);
+            rhs = fma(-g[2], f2p.v[u] - f2m.v[u], rhs);
+            out.v[u] = fma(p.dt, rhs, fv);                                    // solver.cpp:207
+            accDens += out.v[u];
+        }
+        stv<VEC>(nrow + e, out);
+        if (HALO) {
+            // fused halo exchange: the same registers go to the ghost rows on the peer GPUs
+            // (NVLink peer stores), so the transfer overlaps the sweep tile by tile
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (push[q]) stv<VEC>(push[q] + e, out);
+        }
+
+        e += de;
+        i1 += dI1;
+        pl += dPl;
+        if (i1 >= n1) {
+            i1 -= n1;
+            pl++;
+        }
+    }
+}
+
+template <int VEC, bool SHFL, bool UPWIND, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_full_step(const StepParams p)
 {
     extern __shared__ double sm[];
     __shared__ TetRec rec;
@@ -124,142 +238,46 @@ __global__ void __launch_bounds__(256) k_full_step(const StepParams p)
         int* s = reinterpret_cast<int*>(&rec);
         for (int i = tid; i < (int)(sizeof(TetRec) / 4); i += blockDim.x) s[i] = g[i];
     }
-    double* v0 = sm;                   // [n0]
-    double* bl = sm + p.n0;            // [nLines][4]
+    double* v0 = sm;                          // [n0] (padded to an even count)
+    double* bl = sm + ((p.n0 + 1) & ~1);      // [nLines][4]
     // velocity_grid.cpp:30: v = min + i*step, two roundings as in the reference
     for (int i = tid; i < p.n0; i += blockDim.x) v0[i] = __dadd_rn(p.vmin[0], __dmul_rn((double)i, p.step[0]));
     __syncthreads();
     for (int l = tid; l < nLines; l += blockDim.x) {
-        int i1 = l % p.n1;
-        int i2 = pl0 + l / p.n1;
-        double v1 = __dadd_rn(p.vmin[1], __dmul_rn((double)i1, p.step[1]));
-        double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)i2, p.step[2]));
+        const int i1 = l % p.n1;
+        const int i2 = pl0 + l / p.n1;
+        const double v1 = __dadd_rn(p.vmin[1], __dmul_rn((double)i1, p.step[1]));
+        const double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)i2, p.step[2]));
 #pragma unroll
-        for (int f = 0; f < 4; f++) bl[4 * l + f] = rec.nrm[f][1] * v1 + rec.nrm[f][2] * v2;
+        for (int f = 0; f < 4; f++) {
+            const double b = rec.nrm[f][1] * v1 + rec.nrm[f][2] * v2;
+            bl[4 * l + f] = (UPWIND && is_pair(rec.bc[f])) ? rec.coef[f] * b : b;
+        }
     }
     __syncthreads();
 
     const int c0 = tid % p.nvec0;
     const int lg = tid / p.nvec0;
-    const bool active = lg < p.nLG;
 
     double accDens = 0.0;
     double accWall[4] = {0.0, 0.0, 0.0, 0.0};
-
-    if (active) {
-        const int i0 = c0 * VEC;
-        // per-thread part of v.n
-        double a[4][VEC];
-#pragma unroll
-        for (int f = 0; f < 4; f++)
-#pragma unroll
-            for (int u = 0; u < VEC; u++) a[f][u] = rec.nrm[f][0] * v0[i0 + u];
-
-        const double* frow = p.f + (size_t)tet * p.N;
-        double* nrow = p.fn + (size_t)tet * p.N;
-        const double* nb_row[4];
-#pragma unroll
-        for (int f = 0; f < 4; f++) {
-            int n = rec.nbr[f];
-            nb_row[f] = n >= 0 ? p.f + (size_t)n * p.N : (n <= -2 ? p.src + (size_t)(-2 - n) * p.N : nullptr);
-        }
-        // force_k / (2 step_k): (q/m)*(E_k+ext_k) as solver.cpp:193-194
-        double g[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) g[k] = (p.qm * (p.E[3 * (size_t)tet + k] + p.ext[k])) * p.inv2h[k];
-
-        const int plane = p.n0 * p.n1;
-        // x-neighbour offsets (periodic wrap, solver.cpp:380-389)
-        const int offL = (i0 == 0) ? (p.n0 - 1) : -1;                          // left of the first element
-        const int offR = (VEC - 1) + ((i0 + VEC == p.n0) ? -(p.n0 - 1) : 1);   // right of the last element
-        int bcs[4];
-        double coef[4];
-        bool collect[4];
-#pragma unroll
-        for (int f = 0; f < 4; f++) {
-            bcs[f] = rec.bc[f];
-            coef[f] = rec.coef[f];
-            collect[f] = rec.wallSlot[f] >= 0;
-        }
-
-        for (int l = lg; l < nLines; l += p.nLG) {
-            const int i1 = l % p.n1;
-            const int i2 = pl0 + l / p.n1;
-            const int e = (i2 * p.n1 + i1) * p.n0 + i0;
-
-            Vec<VEC> fc = ldv<VEC>(frow + e);
-            // neighbour tets first: longest latency
-            Vec<VEC> fa[4];
-#pragma unroll
-            for (int f = 0; f < 4; f++) {
-                fa[f].x = 0.0;
-                if (VEC == 2) ((double*)&fa[f])[VEC - 1] = 0.0;
-                if (nb_row[f]) fa[f] = ldv_stream<VEC>(nb_row[f] + e);
-            }
-
-            // own-row stencil
-            const int e1m = e + ((i1 == 0) ? (p.n1 - 1) : -1) * p.n0;
-            const int e1p = e + ((i1 == p.n1 - 1) ? -(p.n1 - 1) : 1) * p.n0;
-            const int e2m = e + ((i2 == 0) ? (p.n2 - 1) : -1) * plane;
-            const int e2p = e + ((i2 == p.n2 - 1) ? -(p.n2 - 1) : 1) * plane;
-            Vec<VEC> f1m = ldv<VEC>(frow + e1m), f1p = ldv<VEC>(frow + e1p);
-            Vec<VEC> f2m = ldv<VEC>(frow + e2m), f2p = ldv<VEC>(frow + e2p);
-            double fl, fr;  // left of first element, right of last element
-            if (SHFL) {
-                const double last = (VEC == 2) ? ((const double*)&fc)[VEC - 1] : fc.x;
-                fl = __shfl_sync(0xffffffffu, last, (c0 + p.nvec0 - 1) & (p.nvec0 - 1), p.nvec0);
-                fr = __shfl_sync(0xffffffffu, fc.x, (c0 + 1) & (p.nvec0 - 1), p.nvec0);
-            } else {
-                fl = __ldg(frow + e + offL);
-                fr = __ldg(frow + e + offR);
-            }
-
-            const double* fcv = (const double*)&fc;
-            double out[VEC];
-#pragma unroll
-            for (int u = 0; u < VEC; u++) {
-                const double fv = fcv[u];
-                double rhs = 0.0;
-#pragma unroll
-                for (int f = 0; f < 4; f++) {
-                    const double vn = a[f][u] + bl[4 * l + f];
-                    const int bc = bcs[f];
-                    double flux;
-                    if (bc == VT_PBC_NONBOUNDARY || bc == VT_PBC_PERIODIC || bc == VT_PBC_SOURCE) {
-                        flux = flux_pair(vn, ((const double*)&fa[f])[u], fv);
-                    } else if (bc == VT_PBC_ABSORBING) {
-                        flux = flux_absorb(vn, fv);
-                        if (collect[f]) accWall[f] += flux;
-                    } else {
-                        flux = vn * fv;  // Free, solver.cpp:342
-                    }
-                    rhs = rhs - coef[f] * flux;  // solver.cpp:168
-                }
-                // d/dv0
-                const double xm = (u == 0) ? fl : fcv[u - 1];
-                const double xp = (u == VEC - 1) ? fr : fcv[u + 1];
-                rhs = rhs - g[0] * (xp - xm);
-                rhs = rhs - g[1] * (((const double*)&f1p)[u] - ((const double*)&f1m)[u]);
-                rhs = rhs - g[2] * (((const double*)&f2p)[u] - ((const double*)&f2m)[u]);
-                out[u] = fv + p.dt * rhs;  // solver.cpp:207
-                accDens += out[u];
-            }
-            Vec<VEC> o;
-            o.x = out[0];
-            if (VEC == 2) ((double*)&o)[1] = out[VEC - 1];
-            stv<VEC>(nrow + e, o);
-        }
+    const bool allPair = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]);
+    if (lg < p.nLG) {
+        const bool halo = rec.pushPeer[0] >= 0;
+        if (allPair && !halo) line_loop<VEC, SHFL, false, UPWIND, false>(p, rec, tet, c0, lg, pl0, nLines, v0, bl, accDens, accWall);
+        else if (allPair) line_loop<VEC, SHFL, false, UPWIND, true>(p, rec, tet, c0, lg, pl0, nLines, v0, bl, accDens, accWall);
+        else line_loop<VEC, false, true, UPWIND, true>(p, rec, tet, c0, lg, pl0, nLines, v0, bl, accDens, accWall);
     }
 
     // ---- reductions: sum_v f' for Density(), sum_v flux for the wall charge
     const bool anyWall = (rec.wallSlot[0] >= 0) | (rec.wallSlot[1] >= 0) | (rec.wallSlot[2] >= 0) | (rec.wallSlot[3] >= 0);
     const int warp = tid >> 5, lane = tid & 31;
-    double s = warp_sum(accDens);
+    const double s = warp_sum(accDens);
     if (lane == 0) red[warp][0] = s;
     if (anyWall) {
 #pragma unroll
         for (int f = 0; f < 4; f++) {
-            double w = warp_sum(accWall[f]);
+            const double w = warp_sum(accWall[f]);
             if (lane == 0) red[warp][1 + f] = w;
         }
     }
@@ -284,7 +302,7 @@ __global__ void __launch_bounds__(256) k_full_step(const StepParams p)
 __global__ void k_density_reduce(const double* __restrict__ partial, double* __restrict__ density,
                                  int nOwned, int nChunks, double cellVolume)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nOwned) return;
     double s = 0.0;
     for (int c = 0; c < nChunks; c++) s += partial[(size_t)t * nChunks + c];
@@ -347,7 +365,7 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
     int cp = ctx->chunkPlanes > 0 ? ctx->chunkPlanes : sp.n[2];
     if (cp > sp.n[2]) cp = sp.n[2];
     // keep the per-line table within shared memory
-    while ((size_t)(sp.n[0] + 4 * cp * sp.n[1]) * 8 > 160 * 1024 && cp > 1) cp = (cp + 1) / 2;
+    while ((size_t)(sp.n[0] + 2 + 4 * cp * sp.n[1]) * 8 > 160 * 1024 && cp > 1) cp = (cp + 1) / 2;
     p.chunkPlanes = cp;
     p.nChunks = (sp.n[2] + cp - 1) / cp;
     p.brickTets = ctx->brickTets > 0 ? ctx->brickTets : ctx->nOwned;
@@ -361,22 +379,26 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
     p.qm = sp.charge / sp.mass;
     p.dt = dt;
     p.wallScale = sp.charge * dt * sp.cellVolume;
+    for (int i = 0; i < kMaxPeers; i++) p.peerFn[i] = i < sp.nPeers ? sp.peerF[i][sp.cur ^ 1] : nullptr;
 
-    size_t need = (size_t)ctx->nOwned * p.nChunks;
+    const size_t need = (size_t)ctx->nOwned * p.nChunks;
     if ((size_t)sp.densPartialCap < need) {
         if (sp.densPartial) VT_CUDA(cudaFree(sp.densPartial));
+        sp.densPartial = nullptr;
         VT_CUDA(cudaMalloc(&sp.densPartial, need * sizeof(double)));
         sp.densPartialCap = (int)need;
     }
     p.densPartial = sp.densPartial;
 
-    const size_t smem = (size_t)(sp.n[0] + 4 * cp * sp.n[1]) * sizeof(double);
+    const size_t smem = (size_t)(((sp.n[0] + 1) & ~1) + 4 * cp * sp.n[1]) * sizeof(double);
     const long long grid = (long long)ctx->nOwned * p.nChunks;
     if (grid > 2147483647LL) throw std::runtime_error("vt_step_full: grid too large");
     const int nLines = cp * sp.n[1];
     const bool pow2 = (p.nvec0 & (p.nvec0 - 1)) == 0;
+    // variant bit 0: disable the shuffle path; bit 1: upwind-select arithmetic
     const bool shfl = VEC == 2 && pow2 && p.nvec0 <= 32 && p.nLG * p.nvec0 == threads &&
-                      (nLines % p.nLG == 0) && (sp.n[2] % cp == 0) && ctx->variant == 0;
+                      (nLines % p.nLG == 0) && (sp.n[2] % cp == 0) && !(ctx->variant & 1);
+    const bool upwind = (ctx->variant & 2) != 0;
 
     auto launch = [&](auto kern) {
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -396,9 +418,18 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
         kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
         VT_CUDA(cudaEventRecord(e1, ctx->stream));
     };
-    if (VEC == 2 && shfl) launch(k_full_step<2, true>);
-    else if (VEC == 2) launch(k_full_step<2, false>);
-    else launch(k_full_step<1, false>);
+    // variant bit 2: ask the compiler for 3 resident CTAs per SM (<= 85 registers) instead of 2
+    const bool dense = (ctx->variant & 4) != 0;
+    if (VEC == 2 && shfl) {
+        if (upwind) dense ? launch(k_full_step<2, true, true, 3>) : launch(k_full_step<2, true, true, 2>);
+        else dense ? launch(k_full_step<2, true, false, 3>) : launch(k_full_step<2, true, false, 2>);
+    } else if (VEC == 2) {
+        if (upwind) dense ? launch(k_full_step<2, false, true, 3>) : launch(k_full_step<2, false, true, 2>);
+        else dense ? launch(k_full_step<2, false, false, 3>) : launch(k_full_step<2, false, false, 2>);
+    } else {
+        if (upwind) launch(k_full_step<1, false, true, 2>);
+        else launch(k_full_step<1, false, false, 2>);
+    }
     ctx->launches++;
     VT_CUDA(cudaGetLastError());
 

@@ -146,6 +146,8 @@ void rebuild_tet_records(vt_ctx* ctx, vt::Species& sp)
             const int bc = sp.bcType.empty() ? VT_PBC_NONBOUNDARY : sp.bcType[fi];
             r.bc[j] = (uint8_t)bc;
             r.wallSlot[j] = -1;
+            r.pushPeer[j] = sp.pushPeer.empty() ? -1 : sp.pushPeer[fi];
+            r.pushRow[j] = sp.pushRow.empty() ? -1 : sp.pushRow[fi];
             r.nbr[j] = ctx->nbrHost[4 * (size_t)p + j];
             if (bc == VT_PBC_SOURCE) {
                 const int sid = sp.sourceId.empty() ? -1 : sp.sourceId[fi];
@@ -170,6 +172,17 @@ void rebuild_tet_records(vt_ctx* ctx, vt::Species& sp)
                 sp.danglingFaces++;
             }
         }
+        // halo push slots are not tied to faces: pack the used ones to the front
+        int used = 0;
+        for (int j = 0; j < 4; j++)
+            if (r.pushPeer[j] >= 0) {
+                const int32_t pp = r.pushPeer[j], pr = r.pushRow[j];
+                r.pushPeer[j] = -1;
+                r.pushRow[j] = -1;
+                r.pushPeer[used] = pp;
+                r.pushRow[used] = pr;
+                used++;
+            }
     }
     if (!sp.rec) VT_CUDA(cudaMalloc(&sp.rec, std::max<size_t>(1, n) * sizeof(vt::TetRec)));
     VT_CUDA(cudaMemcpy(sp.rec, sp.recHost.data(), (size_t)n * sizeof(vt::TetRec), cudaMemcpyHostToDevice));
@@ -182,6 +195,8 @@ void rebuild_tet_records(vt_ctx* ctx, vt::Species& sp)
 }  // namespace
 
 namespace vt {
+void rebuild_tet_records_public(vt_ctx* ctx, Species& sp) { rebuild_tet_records(ctx, sp); }
+
 double* ctx_stage(vt_ctx* ctx, size_t bytes)
 {
     if (ctx->stageBytes < bytes) {
@@ -207,6 +222,7 @@ double* ctx_pinned(vt_ctx* ctx, size_t bytes)
 extern "C" {
 
 const char* vt_last_error(void) { return g_err.c_str(); }
+void vt_set_error(const char* msg) { g_err = msg; }
 int vt_version(void) { return 100; }
 
 int vt_ctx_create(int device, vt_ctx** out)
@@ -244,6 +260,9 @@ void vt_ctx_destroy(vt_ctx* ctx)
         cudaFree(sp->wall);
         delete sp;
     }
+    for (void* p : ctx->ipcOpened) cudaIpcCloseMemHandle(p);
+    cudaFree(ctx->flags);
+    cudaFree(ctx->haloStatus);
     if (ctx->poisson) vt::poisson_destroy(ctx->poisson);
     cudaFree(ctx->E);
     cudaFree(ctx->rho);
@@ -263,6 +282,11 @@ int vt_sync(vt_ctx* ctx)
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->haloStatus) {
+            int st = 0;
+            VT_CUDA(cudaMemcpy(&st, ctx->haloStatus, sizeof(int), cudaMemcpyDeviceToHost));
+            if (st) throw std::runtime_error("halo barrier timed out: a peer rank did not reach the step barrier");
+        }
     });
 }
 
@@ -341,6 +365,8 @@ int vt_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], con
             VT_CUDA(cudaMemsetAsync(sp->f[b], 0, rows * sp->N * sizeof(double), ctx->stream));
         }
         VT_CUDA(cudaMalloc(&sp->density, std::max(1, ctx->nOwned) * sizeof(double)));
+        // the buffers may be exported to peer GPUs right away: nothing of ours may still be pending
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
         ctx->species.push_back(sp);
         rebuild_tet_records(ctx, *sp);
         *species = (int)ctx->species.size() - 1;

@@ -28,7 +28,13 @@ struct TetRec {
     uint8_t bc[4];       // ParticleBCType                      (solver.h:25)
     int8_t wallSlot[4];  // >= 0: Absorbing && collectCharge -> accumulator slot (solver.cpp:171)
     double area[4];      // face->area (wall charge)            (solver.cpp:173)
+    // multi-GPU halo: this tet is a ghost row on up to 4 peer GPUs; the step kernel stores its
+    // new state there as well (peer index into StepParams::peerFn, row in the peer's buffer)
+    int32_t pushPeer[4]; // -1 = unused
+    int32_t pushRow[4];
 };
+
+constexpr int kMaxPeers = 16;
 
 struct StepParams {
     const double* f;      // state at step n, rows of N doubles (owned then ghost)
@@ -48,6 +54,7 @@ struct StepParams {
     double ext[3];
     double dt;
     double wallScale;     // charge * dt * cellVolume
+    double* peerFn[kMaxPeers];   // peers' step-n+1 buffers (CUDA-IPC mapped), for the halo push
 };
 
 struct Species {
@@ -70,6 +77,10 @@ struct Species {
     std::vector<uint8_t> bcType, collect;
     std::vector<int32_t> sourceId;
     int danglingFaces = 0;            // boundary faces with neither neighbour nor particle BC
+    // halo (multi-GPU): peers' ping-pong buffers opened through CUDA IPC
+    int nPeers = 0;
+    double* peerF[kMaxPeers][2] = {};
+    std::vector<int32_t> pushPeer, pushRow;   // 4 per owned tet, caller order, -1 unused
 };
 
 struct PoissonData;
@@ -111,7 +122,18 @@ struct vt_ctx {
     int chunkPlanes = 0, brickTets = 0, variant = 0;
 
     vt::PoissonData* poisson = nullptr;
+
+    // multi-GPU: flag words for the device-side barrier between steps (CUDA-IPC shared)
+    int rank = 0, nPeers = 0;
+    int peerRank[vt::kMaxPeers] = {};
+    uint32_t* flags = nullptr;                       // [64] one word per source rank, local
+    uint32_t* peerFlags[vt::kMaxPeers] = {};         // peers' flag arrays
+    uint32_t epoch = 0;
+    int* haloStatus = nullptr;                       // device: != 0 when a barrier timed out
+    std::vector<void*> ipcOpened;
 };
+
+extern "C" void vt_set_error(const char* msg);   // internal: sets vt_last_error()
 
 namespace vt {
 void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3]);
