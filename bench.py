@@ -283,7 +283,7 @@ def run_gpu(args):
                             f"x {nv}^3 velocity nodes, full format, electrons (Maxwellian 1 eV, 1% density wave), dt=1e-3 T_p",
                 "tets_per_gpu": nT, "v_nodes": N, "state_bytes_per_gpu": 2 * nT * N * 8,
                 "l2_policy": "inputs larger than L2 (state is %.1f GB per copy); no flush needed" % (nT * N * 8 / 1e9),
-                "brick_hexes": list(args.brick), "chunk_planes": args.chunk_planes,
+                "brick_hexes": list(args.brick), "chunk_planes": args.chunk_planes, "kernel_variant": args.variant,
                 "step": "K1 full_step (flux+accel+Euler+density partials) + density reduce" + ("; halo push over NVLink" if world > 1 else ""),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -314,9 +314,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--hexes", type=int, nargs=3, default=[28, 28, 28], help="hexes per GPU block")
     ap.add_argument("--nv", type=int, default=32)
-    ap.add_argument("--brick", type=int, nargs=3, default=[7, 7, 7], help="L2 brick in hexes")
-    ap.add_argument("--chunk-planes", type=int, default=2)
-    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--brick", type=int, nargs=3, default=[4, 4, 4], help="L2 brick in hexes")
+    ap.add_argument("--chunk-planes", type=int, default=0, help="i2-planes per work item (0 = whole tensor)")
+    ap.add_argument("--variant", type=int, default=2, help="vt_step_config variant bits (2 = upwind-select arithmetic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

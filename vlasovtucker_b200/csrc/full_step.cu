@@ -329,6 +329,9 @@ __global__ void k_density_full(const double* __restrict__ f, double* __restrict_
 
 }  // namespace
 
+bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, cudaEvent_t e0, cudaEvent_t e1);
+bool launch_full_step_async(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, cudaEvent_t e0, cudaEvent_t e1);
+
 void launch_density(vt_ctx* ctx, Species& sp)
 {
     if (ctx->nOwned == 0) return;
@@ -400,27 +403,36 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
                       (nLines % p.nLG == 0) && (sp.n[2] % cp == 0) && !(ctx->variant & 1);
     const bool upwind = (ctx->variant & 2) != 0;
 
+    cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
+    if (ctx->profiling) {
+        if (ctx->kernelEventsUsed + 2 > ctx->kernelEvents.size()) {
+            cudaEvent_t a, b;
+            VT_CUDA(cudaEventCreate(&a));
+            VT_CUDA(cudaEventCreate(&b));
+            ctx->kernelEvents.push_back(a);
+            ctx->kernelEvents.push_back(b);
+        }
+        e0 = ctx->kernelEvents[ctx->kernelEventsUsed++];
+        e1 = ctx->kernelEvents[ctx->kernelEventsUsed++];
+    }
     auto launch = [&](auto kern) {
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
-        if (ctx->profiling) {
-            if (ctx->kernelEventsUsed + 2 > ctx->kernelEvents.size()) {
-                cudaEvent_t a, b;
-                VT_CUDA(cudaEventCreate(&a));
-                VT_CUDA(cudaEventCreate(&b));
-                ctx->kernelEvents.push_back(a);
-                ctx->kernelEvents.push_back(b);
-            }
-            e0 = ctx->kernelEvents[ctx->kernelEventsUsed++];
-            e1 = ctx->kernelEvents[ctx->kernelEventsUsed++];
-        }
         VT_CUDA(cudaEventRecord(e0, ctx->stream));
         kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
         VT_CUDA(cudaEventRecord(e1, ctx->stream));
     };
+    // variant bit 3: force the register-staged kernel even where the TMA pipeline applies
+    // bit 3: the persistent cp.async pipeline; bit 4: the persistent bulk-copy (TMA) producer.
+    // Both are measured slower than the register-staged kernel on B200 (profiles/round1_notes.md)
+    // and stay opt-in; they fall through to the register-staged kernel where they do not apply.
+    bool useTma = false;
+    if (ctx->variant & 16) useTma = launch_full_step_tma(ctx, sp, p, upwind, e0, e1);
+    else if (ctx->variant & 8) useTma = launch_full_step_async(ctx, sp, p, upwind, e0, e1);
     // variant bit 2: ask the compiler for 3 resident CTAs per SM (<= 85 registers) instead of 2
     const bool dense = (ctx->variant & 4) != 0;
-    if (VEC == 2 && shfl) {
+    if (useTma) {
+        // launched above
+    } else if (VEC == 2 && shfl) {
         if (upwind) dense ? launch(k_full_step<2, true, true, 3>) : launch(k_full_step<2, true, true, 2>);
         else dense ? launch(k_full_step<2, true, false, 3>) : launch(k_full_step<2, true, false, 2>);
     } else if (VEC == 2) {

@@ -169,15 +169,12 @@ int vt_halo_barrier(vt_ctx* ctx)
             tb.pf[i] = ctx->peerFlags[i];
             tb.pr[i] = ctx->peerRank[i];
         }
-        static_assert(sizeof(Table) <= 4096, "table size");
-        // reuse a dedicated tiny allocation (the stage buffer may be in use by other calls)
-        static thread_local Table* tableDev = nullptr;
-        static thread_local vt_ctx* tableOwner = nullptr;
-        if (!tableDev || tableOwner != ctx) {
-            VT_CUDA(cudaMalloc(&tableDev, sizeof(Table)));
-            tableOwner = ctx;
-            VT_CUDA(cudaMemcpy(tableDev, &tb, sizeof(tb), cudaMemcpyHostToDevice));
+        // a dedicated tiny allocation owned by the context (the stage buffer may be in use)
+        if (!ctx->haloTable) {
+            VT_CUDA(cudaMalloc(&ctx->haloTable, sizeof(Table)));
+            VT_CUDA(cudaMemcpy(ctx->haloTable, &tb, sizeof(tb), cudaMemcpyHostToDevice));
         }
+        Table* tableDev = static_cast<Table*>(ctx->haloTable);
         uint32_t* const* pfDev = reinterpret_cast<uint32_t* const*>(tableDev);
         const int* prDev = reinterpret_cast<const int*>(reinterpret_cast<const char*>(tableDev) + sizeof(tb.pf));
         k_halo_barrier<<<1, 32, 0, ctx->stream>>>(ctx->flags, pfDev, prDev, ctx->nPeers, ctx->rank, ctx->epoch,

@@ -263,6 +263,8 @@ void vt_ctx_destroy(vt_ctx* ctx)
     for (void* p : ctx->ipcOpened) cudaIpcCloseMemHandle(p);
     cudaFree(ctx->flags);
     cudaFree(ctx->haloStatus);
+    cudaFree(ctx->haloTable);
+    cudaFree(ctx->workCounter);
     if (ctx->poisson) vt::poisson_destroy(ctx->poisson);
     cudaFree(ctx->E);
     cudaFree(ctx->rho);

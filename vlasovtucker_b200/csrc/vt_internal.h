@@ -32,7 +32,9 @@ struct TetRec {
     // new state there as well (peer index into StepParams::peerFn, row in the peer's buffer)
     int32_t pushPeer[4]; // -1 = unused
     int32_t pushRow[4];
+    int32_t pad[2];      // sizeof == 224: records are copied with 16-byte cp.async
 };
+static_assert(sizeof(TetRec) == 224, "TetRec must stay a multiple of 16 bytes");
 
 constexpr int kMaxPeers = 16;
 
@@ -120,6 +122,7 @@ struct vt_ctx {
     size_t pinnedBytes = 0;
 
     int chunkPlanes = 0, brickTets = 0, variant = 0;
+    unsigned long long* workCounter = nullptr;   // device: head of the persistent kernel's work queue
 
     vt::PoissonData* poisson = nullptr;
 
@@ -131,6 +134,7 @@ struct vt_ctx {
     uint32_t epoch = 0;
     int* haloStatus = nullptr;                       // device: != 0 when a barrier timed out
     std::vector<void*> ipcOpened;
+    void* haloTable = nullptr;                       // device copy of the peer flag pointers/ranks
 };
 
 extern "C" void vt_set_error(const char* msg);   // internal: sets vt_last_error()
