@@ -124,7 +124,7 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_baseline(steps=2, warmup=1, hexes=(6, 6, 6), nv=32, threads=None, fused=False):
+def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fused=False):
     """The oracle's reference-faithful restatement of _UpdatePDF (one temporary per tensor
     operator, OpenMP over tets as src/solver.cpp:159,187,204) on a bounded sample of C4."""
     threads = threads or os.cpu_count() or 1
@@ -142,8 +142,12 @@ def cpu_baseline(steps=2, warmup=1, hexes=(6, 6, 6), nv=32, threads=None, fused=
     s.set_params(sp, cfg["dt"], fused=fused)
     E = np.zeros((m.nTets, 3))
     E[:, 0] = 1e3 * np.cos(2 * PI * x)
+    tw = time.perf_counter()
     for _ in range(warmup):
         s.update_pdf(sp, E)
+    tw = (time.perf_counter() - tw) / max(1, warmup)
+    if steps is None:   # bounded sample: about 12 s of CPU work
+        steps = int(min(40, max(2, round(12.0 / max(tw, 1e-3)))))
     t0 = time.perf_counter()
     for _ in range(steps):
         s.update_pdf(sp, E)

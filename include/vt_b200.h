@@ -68,6 +68,9 @@ int vt_mesh_upload(vt_ctx* ctx, int nOwned, int nGhost, const int32_t* nbr, cons
  */
 int vt_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], const double vmax[3],
                       double mass, double charge, int* species);
+/* ParticleData::mass / ::charge are public members the drivers assign after construction
+ * (examples/oscillations.cpp:32-33); push the current values before they are used */
+int vt_species_set_params(vt_ctx* ctx, int species, double mass, double charge);
 /* Solver::SetParticleBC (src/solver.cpp:62-71): per-face BC type (uint8, 4 per tet), the
  * collectCharge flag, and for Source faces an index into the source-PDF table (-1 otherwise). */
 int vt_species_set_face_bc(vt_ctx* ctx, int species, const uint8_t* bcType, const uint8_t* collect,

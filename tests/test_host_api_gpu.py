@@ -1,0 +1,84 @@
+"""The C++ host classes (vlasovtucker_b200/host/, the reference's API names over the C ABI)
+driven exactly as examples/oscillations.cpp and examples/sheath.cpp drive the reference, then
+compared with the oracle.  The binary is built by __graft_entry__.build() (make parity)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, mesh_path, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "vlasovtucker_b200", "build", "host_parity")
+EPS0 = 8.85e-12
+PI = 3.14159265358979323846
+
+
+def _run(case, mesh, iters, tmp_path):
+    if not os.path.exists(BIN):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "vlasovtucker_b200", "host"), "parity"])
+    out = str(tmp_path / f"{case}.bin")
+    r = subprocess.run([BIN, case, mesh_path(mesh), str(iters), out], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return np.fromfile(out)
+
+
+def _split(buf, nT, N):
+    f = buf[:nT * N].reshape(nT, N)
+    dens = buf[nT * N:nT * N + nT]
+    vel = buf[nT * N + nT:nT * N + 4 * nT].reshape(nT, 3)
+    return f, dens, vel, buf[nT * N + 4 * nT:]
+
+
+@pytest.mark.parametrize("mesh,iters", [("fully_periodic_coarse.msh", 25), ("rectangle.msh", 25)])
+def test_oscillations_driver(oracle_mod, tmp_path, mesh, iters):
+    m = oracle_mod.Mesh.load(mesh_path(mesh), [(1, 2), (3, 4), (5, 6)])
+    buf = _run("oscillations", mesh, iters, tmp_path)
+    f, dens, vel, rest = _split(buf, m.nTets, 1331)
+    assert rest.size == 0
+    q = 2.975e-5
+    L = m.points[:, 0].max()
+    s = oracle_mod.Sim(m)
+    sp = s.add_species((11, 11, 11), [-3, -.1, -.1], [3, .1, .1], 1.0, q)
+    s.set_maxwell(sp, 10 + 0.2 * np.sin(m.tetCentroid[:, 0] / L * (2 * PI)), 0.0)
+    s.set_params(sp, 1e-4, background=np.full(m.nTets, -q * 10), fused=True)
+    s.begin()
+    for it in range(iters):
+        s.step(it)
+    assert rel_l2(f, s.get_pdf(sp)) <= 1e-10
+    assert rel_l2(dens, s.density(sp)) <= 1e-10
+    assert np.abs(vel - s.velocity(sp)).max() <= 1e-8 * max(1e-300, np.abs(s.velocity(sp)).max())
+
+
+def test_sheath_driver(oracle_mod, tmp_path):
+    kB, e, me, mi, eV = 1.38e-23, 1.6e-19, 9.1e-31, 1.66e-27, 11604.518
+    Te, Ti, dens0 = 1 * eV, 400.0, 1e17
+    debye = np.sqrt(EPS0 * kB * Te / dens0) / e
+    wp = e * np.sqrt(dens0 / (me * EPS0))
+    dt = 1e-4 * (2 * PI / wp)
+    iters = 21
+    m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(3, 4), (5, 6)], scale=22 * debye)
+    buf = _run("sheath", "rectangle_fine.msh", iters, tmp_path)
+    fe, de, ve, rest = _split(buf, m.nTets, 1250)
+    fi, di, vi, rest = _split(rest, m.nTets, 1250)
+    assert rest.size == 0
+    maxVE = np.sqrt(-np.log(1e-6) * 2 * kB * Te / me)
+    maxVI = np.sqrt(-np.log(1e-6) * 2 * kB * Ti / mi)
+    s = oracle_mod.Sim(m)
+    for (vmax, mass, q, T, mult) in [(maxVE, me, -e, Te, 1), (maxVI, mi, e, Ti, 10)]:
+        sp = s.add_species((50, 5, 5), [-4 * vmax, -vmax, -vmax], [4 * vmax, vmax, vmax], mass, q, mult)
+        s.set_maxwell(sp, np.full(m.nTets, dens0), T)
+        s.set_params(sp, dt * mult, fused=True)
+        s.set_particle_bc(sp, 1, "Absorbing", True)
+        s.set_particle_bc(sp, 2, "Free", False)
+    s.set_field_bc_charge(0, 1, 0.0)
+    s.set_field_bc_potential(0, 2, 0.0)
+    s.begin()
+    for it in range(iters):
+        s.step(it)
+    assert rel_l2(fe, s.get_pdf(0)) <= 1e-10
+    assert rel_l2(fi, s.get_pdf(1)) <= 1e-10
+    assert rel_l2(de, s.density(0)) <= 1e-10
+    assert rel_l2(di, s.density(1)) <= 1e-10

@@ -26,6 +26,7 @@ SIGNATURES = {
     "vt_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "vt_mesh_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_ip, c_dp, c_dp, c_dp, c_ip, c_ip]),
     "vt_species_create": (C.c_int, [C.c_void_p, c_ip, c_dp, c_dp, C.c_double, C.c_double, C.POINTER(C.c_int)]),
+    "vt_species_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double]),
     "vt_species_set_face_bc": (C.c_int, [C.c_void_p, C.c_int, c_u8p, c_u8p, c_ip]),
     "vt_species_set_source_pdfs": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp]),
     "vt_species_set_pdf": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]),

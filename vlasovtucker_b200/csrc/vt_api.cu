@@ -375,6 +375,15 @@ int vt_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], con
     });
 }
 
+int vt_species_set_params(vt_ctx* ctx, int species, double mass, double charge)
+{
+    return guard([&] {
+        vt::Species& sp = species_of(ctx, species);
+        sp.mass = mass;
+        sp.charge = charge;
+    });
+}
+
 int vt_species_set_face_bc(vt_ctx* ctx, int species, const uint8_t* bcType, const uint8_t* collect,
                            const int32_t* sourceId)
 {

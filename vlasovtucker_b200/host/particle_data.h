@@ -1,0 +1,64 @@
+// Per-species state of the public API (reference: src/particle_data.h:21-59).  For
+// TensorType = Full the distribution function lives on the GPU and `pdf` holds row handles;
+// for TensorType = Tucker `pdf` holds host values (the device Tucker path is under construction).
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "constants.h"
+#include "mesh.h"
+#include "typedefs.h"
+#include "velocity_grid.h"
+
+namespace VlasovTucker {
+namespace device {
+struct MeshContext;
+}
+
+struct MaxwellPDF {
+    std::vector<double> physDensity;
+    double temperature;
+    Vector3d mostProbableV;
+};
+
+template <typename TensorType>
+class ParticleData {
+public:
+    ParticleData(const Mesh* mesh, const VelocityGrid* vGrid);
+
+    void SetMaxwellPDF(const MaxwellPDF& paramsPDF);
+
+    std::vector<double> Density() const;
+    std::vector<Vector3d> Velocity() const;
+
+    void SetCompressionError(double error);
+    double CompressionError() const;
+    int MaxRank() const;
+    void SetMaxRank(int maxRank);   // addition: fixed-rank configurations
+
+    // device binding (not in the reference API)
+    std::shared_ptr<device::MeshContext> DeviceContext() const { return _dev; }
+    int DeviceSpecies() const { return _species; }
+    void PushParams() const;        // mass/charge are public members assigned after construction
+
+public:
+    std::string species = "";
+    double mass;
+    double charge;
+    std::vector<TensorType> pdf;
+
+private:
+    const Mesh* _mesh;
+    const VelocityGrid* _vGrid;
+    double _comprErr = 1e-10;
+    int _maxRank;
+    std::shared_ptr<device::MeshContext> _dev;
+    int _species = -1;
+};
+
+std::vector<double> ScalarField(const Mesh* mesh, std::function<double(const Point&)> densityFunc);
+double DebyeLength(double temperature, double density, double charge);
+double PlasmaFrequency(double density, double charge, double mass);
+}  // namespace VlasovTucker

@@ -1,0 +1,61 @@
+// Tucker-format 3-D tensor of the public API (reference: src/tucker.h:9-87): core r0 x r1 x r2
+// plus three factor matrices n_i x r_i.  This host class is the user-facing value type (tests
+// construct it from a Tensor3d, add, scale and round it); the per-step Tucker update of the
+// solver runs on the device.
+#pragma once
+#include <Eigen/Dense>
+#include <array>
+#include <ostream>
+
+#include "typedefs.h"
+
+namespace VlasovTucker {
+class Tucker {
+public:
+    Tucker();
+    Tucker(int n0, int n1, int n2, int r0, int r1, int r2);                        // zero tensor of given ranks
+    Tucker(const Tensor3d& tensor, double precision = 0, int maxRank = 1e+6);     // truncated HOSVD
+    Tucker(const Tensor3d& core, const std::array<Eigen::MatrixXd, 3>& u);
+
+    Tucker& Compress(double precision = 0, int maxRank = 1e+6);
+    Tensor3d Reconstructed() const;
+
+    int Size() const;
+    std::array<int, 3> Dimensions() const;
+    std::array<int, 3> Ranks() const;
+    std::array<Eigen::MatrixXd, 3> U() const;
+    Tensor3d Core() const;
+
+    double Sum() const;
+    double Norm() const;
+
+    double operator()(int i0, int i1, int i2) const;
+
+    Tucker& operator+=(const Tucker& t);
+    Tucker& operator-=(const Tucker& t);
+    Tucker& operator*=(const Tucker& t);
+    Tucker& operator*=(double d);
+
+    friend Tucker operator+(const Tucker& t1, const Tucker& t2);
+    friend Tucker operator-(const Tucker& t1, const Tucker& t2);
+    friend Tucker operator*(const Tucker& t1, const Tucker& t2);   // Hadamard product
+    friend Tucker operator*(double d, const Tucker& t);
+    friend Tucker operator*(const Tucker& t, double d);
+    friend Tucker operator-(const Tucker& t);
+
+    friend std::ostream& operator<<(std::ostream& out, const Tucker& t);
+
+private:
+    void _ComputeU(const Tensor3d& tensor, double precision, int maxRank);
+
+    std::array<int, 3> _n;
+    std::array<int, 3> _r;
+    std::array<Eigen::MatrixXd, 3> _u;
+    Tensor3d _core;
+};
+
+// Mode-`index` unfolding with the reference's column order (tucker.cpp:337-392): mode 0 columns
+// run i2 fastest then i1; mode 1: i0 fastest then i2; mode 2: i1 fastest then i0.
+Eigen::MatrixXd Unfolding(const Tensor3d& tensor, int index);
+Tensor3d Folding(int I0, int I1, int I2, const Eigen::MatrixXd& unfolding, int index);
+}  // namespace VlasovTucker
