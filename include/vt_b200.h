@@ -155,6 +155,26 @@ int vt_poisson_stats(vt_ctx* ctx, int* lastIterations, double* lastRelResidual);
  * src/multicomponent_solver.cpp:61-74); background may be NULL */
 int vt_charge_density(vt_ctx* ctx, const int* species, int nSpecies, const double* background);
 
+/* ---- Tucker format: ParticleData<Tucker> + Solver<Tucker> (src/tucker.cpp, src/solver.cpp) ---- */
+/* switch a species to Tucker storage: ParticleData::SetCompressionError / SetMaxRank
+ * (src/particle_data.cpp:18, 174-185); maxRank <= 0 = max(n) as the reference defaults */
+int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank);
+/* dense rows (nOwned x N, caller order) -> exact Tucker tensors, as ParticleData<Tucker>::
+ * SetMaxwellPDF builds them with precision 0 (src/particle_data.cpp:64-69) */
+int vt_tucker_set_pdf(vt_ctx* ctx, int species, const double* dense);
+/* Tucker::Reconstructed() of every tet (src/tucker.cpp:100-104) */
+int vt_tucker_get_pdf(vt_ctx* ctx, int species, double* dense);
+/* Tucker::Ranks() of every tet, 3 per tet (src/tucker.cpp:126-129) */
+int vt_tucker_get_ranks(vt_ctx* ctx, int species, int32_t* ranks);
+/* Tucker::Core()/U() of one tet; buffers sized for the rank capacity min(maxRank, n_k) */
+int vt_tucker_get_factors(vt_ctx* ctx, int species, int tet, int32_t ranks[3], double* core, double* u0,
+                          double* u1, double* u2);
+/* ParticleData<Tucker>::Density (src/particle_data.cpp:93-102); density may be NULL */
+int vt_tucker_density(vt_ctx* ctx, int species, double* density);
+/* Solver<Tucker>::_UpdatePDF for one species (src/solver.cpp:141-212): flux per face, rounding
+ * after each face, acceleration term, rounding, Euler update, rounding */
+int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3]);
+
 #ifdef __cplusplus
 }
 #endif

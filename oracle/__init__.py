@@ -282,3 +282,112 @@ class Sim:
             lib().orc_sim_free(self.h)
         except Exception:
             pass
+
+
+class TuckerObj:
+    """Restated stand-alone ``Tucker`` tensor (tucker.cpp), as test/tucker_test.cpp uses it."""
+
+    def __init__(self, handle, n):
+        self.h = C.c_void_p(handle)
+        self.n = tuple(int(x) for x in n)
+
+    @classmethod
+    def from_full(cls, x, precision=0.0, rmax=1000000):
+        """x: array of shape (n0, n1, n2); stored i0-fastest like Eigen::Tensor."""
+        x = np.asarray(x, np.float64)
+        n = np.asarray(x.shape, np.int32)
+        flat = np.ascontiguousarray(x.ravel(order="F"))
+        return cls(lib().orc_tucker_from_full(_d(flat), _i(n), C.c_double(precision), int(rmax)), x.shape)
+
+    def clone(self):
+        return TuckerObj(lib().orc_tucker_clone(self.h), self.n)
+
+    def ranks(self):
+        r = np.zeros(3, np.int32)
+        lib().orc_tucker_ranks(self.h, _i(r))
+        return tuple(int(x) for x in r)
+
+    def reconstructed(self):
+        out = np.zeros(self.n[0] * self.n[1] * self.n[2])
+        lib().orc_tucker_reconstruct(self.h, _d(out))
+        return out.reshape(self.n, order="F")
+
+    def compress(self, precision=0.0, rmax=1000000):
+        lib().orc_tucker_compress(self.h, C.c_double(precision), int(rmax))
+        return self
+
+    def sum(self):
+        return lib().orc_tucker_sum(self.h)
+
+    def axpy(self, s, other):
+        """self <- self + s*other (operator+= / operator-= with the scalar product)."""
+        lib().orc_tucker_axpy(self.h, C.c_double(s), other.h)
+        return self
+
+    def hadamard(self, other):
+        lib().orc_tucker_hadamard(self.h, other.h)
+        return self
+
+    def __del__(self):
+        try:
+            lib().orc_tucker_free(self.h)
+        except Exception:
+            pass
+
+
+class TuckerSim:
+    """Restated ``Solver<Tucker>::_UpdatePDF`` + ``ParticleData<Tucker>`` for one species."""
+
+    def __init__(self, mesh, n, vmin, vmax, mass, charge, compr_err, max_rank=0):
+        self.mesh = mesh
+        self.n = tuple(int(x) for x in n)
+        n_ = np.asarray(n, np.int32)
+        vmin_ = np.asarray(vmin, np.float64)
+        vmax_ = np.asarray(vmax, np.float64)
+        L = lib()
+        L.orc_tsim_create.restype = C.c_void_p
+        self.h = C.c_void_p(L.orc_tsim_create(mesh.h, _i(n_), _d(vmin_), _d(vmax_), C.c_double(mass),
+                                              C.c_double(charge), C.c_double(compr_err), int(max_rank)))
+
+    @property
+    def N(self):
+        return self.n[0] * self.n[1] * self.n[2]
+
+    def set_particle_bc(self, entity, kind):
+        lib().orc_tsim_set_particle_bc(self.h, int(entity), PBC[kind])
+
+    def set_pdf(self, f):
+        f = np.ascontiguousarray(f, np.float64)
+        assert f.size == self.mesh.nTets * self.N
+        lib().orc_tsim_set_pdf(self.h, _d(f))
+
+    def get_pdf(self):
+        f = np.zeros((self.mesh.nTets, self.N))
+        lib().orc_tsim_get_pdf(self.h, _d(f))
+        return f
+
+    def ranks(self):
+        r = np.zeros((self.mesh.nTets, 3), np.int32)
+        lib().orc_tsim_ranks(self.h, _i(r))
+        return r
+
+    def vnabs(self, face):
+        out = np.zeros(self.N)
+        lib().orc_tsim_vnabs(self.h, int(face), _d(out))
+        return out
+
+    def update_pdf(self, dt, E, ext=None):
+        E = np.ascontiguousarray(E, np.float64)
+        ext = None if ext is None else np.asarray(ext, np.float64)
+        lib().orc_tsim_update_pdf(self.h, C.c_double(dt), _d(E), _d(ext))
+
+    def density(self):
+        out = np.zeros(self.mesh.nTets)
+        lib().orc_tsim_density(self.h, _d(out))
+        return out
+
+    def __del__(self):
+        try:
+            lib().orc_tsim_free(self.h)
+        except Exception:
+            pass

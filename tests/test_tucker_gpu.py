@@ -1,0 +1,138 @@
+"""Device Tucker path (vt_tucker_*, vt_step_tucker) against the oracle's Tucker algebra
+(oracle/oracle_tucker.cpp) through the C ABI.  Tolerance: the reconstructed tensors and the
+densities agree within comprErr + 1e-10 (relative L2), the bar BASELINE.json states."""
+import numpy as np
+import pytest
+
+from conftest import face_bc_arrays, mesh_path, rel_l2, tables_from_oracle
+from np_ref import vgrid
+import tucker_dense_ref as tdr
+
+pytestmark = pytest.mark.gpu
+
+
+def _initial(m, n, vmin, vmax, drift=0.4):
+    _, V = vgrid(n, vmin, vmax)
+    L = m.points[:, 0].max()
+    dens = 1 + 0.3 * np.sin(2 * np.pi * m.tetCentroid[:, 0] / L)
+    mx = np.exp(-0.5 * ((V[0] - drift) ** 2 + (V[1] / 0.5) ** 2 + (V[2] / 0.5) ** 2))
+    return dens[:, None] * mx[None, :]
+
+
+def _ctx(m, n, vmin, vmax, mass, charge, spec, eps, max_rank=0):
+    import vlasovtucker_b200 as vtb
+    ctx = vtb.Context(0)
+    ctx.mesh_upload(tables_from_oracle(m))
+    g = ctx.species_create(n, vmin, vmax, mass, charge)
+    bc, col = face_bc_arrays(m, spec)
+    ctx.set_face_bc(g, bc, col)
+    ctx.tucker_enable(g, eps, max_rank)
+    return ctx, g, bc
+
+
+def test_set_get_roundtrip(oracle_mod):
+    m = oracle_mod.Mesh.load(mesh_path("fully_periodic_coarse.msh"), [(1, 2), (3, 4), (5, 6)])
+    n = (9, 7, 5)
+    ctx, g, _ = _ctx(m, n, [-1, -1, -1], [1, 1, 1], 1.0, 1.0, {}, 1e-6)
+    rng = np.random.default_rng(0)
+    f = rng.random((m.nTets, 9 * 7 * 5))
+    ctx.tucker_set_pdf(g, f)
+    assert rel_l2(ctx.tucker_get_pdf(g, f.shape[1]), f) <= 1e-12       # precision 0: exact (particle_data.cpp:64-69)
+    assert rel_l2(ctx.tucker_density(g), f.sum(axis=1) * (2 / 8) * (2 / 6) * (2 / 4)) <= 1e-12
+    core, U = ctx.tucker_factors(g, 3, n)
+    for k in range(3):
+        assert np.abs(U[k].T @ U[k] - np.eye(U[k].shape[1])).max() <= 1e-12   # orthonormal factors
+    rec = np.einsum("ijk,ai,bj,ck->abc", core, U[0], U[1], U[2]).ravel(order="F")
+    assert rel_l2(rec, f[3]) <= 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("mesh,pairs,spec", [
+    ("fully_periodic_coarse.msh", [(1, 2), (3, 4), (5, 6)], {}),
+    ("rectangle.msh", [(3, 4), (5, 6)], {1: ("Absorbing", False), 2: ("Free", False)}),
+])
+@pytest.mark.parametrize("eps", [1e-6, 1e-4])
+def test_step_parity(oracle_mod, mesh, pairs, spec, eps):
+    m = oracle_mod.Mesh.load(mesh_path(mesh), pairs)
+    n, vmin, vmax = (9, 7, 5), [-3.0, -1.0, -1.0], [3.0, 1.0, 1.0]
+    dt, mass, charge = 2e-3, 2.0, 1.0
+    f = _initial(m, n, vmin, vmax)
+    E = np.random.default_rng(4).standard_normal((m.nTets, 3))
+    ts = oracle_mod.TuckerSim(m, n, vmin, vmax, mass, charge, eps)
+    for e, (kind, _) in spec.items():
+        ts.set_particle_bc(e, kind)
+    ts.set_pdf(f)
+    ctx, g, bc = _ctx(m, n, vmin, vmax, mass, charge, spec, eps)
+    ctx.tucker_set_pdf(g, f)
+    ctx.field_set(E)
+    for _ in range(3):
+        ts.update_pdf(dt, E)
+        ctx.step_tucker(g, dt)
+    fo, fg = ts.get_pdf(), ctx.tucker_get_pdf(g, f.shape[1])
+    tol = eps + 1e-10
+    assert rel_l2(fg, fo) <= tol
+    assert rel_l2(ctx.tucker_density(g), ts.density()) <= tol
+    assert np.abs(ctx.tucker_ranks(g) - ts.ranks()).max() <= 1
+    # the same formulation in numpy (SVD instead of Gram/Jacobi): far tighter than eps
+    gd = f.copy()
+    for _ in range(3):
+        gd, _ = tdr.step_dense(gd, m.adj, m.faceArea, m.tetVolume, m.faceNormal, bc, n, vmin, vmax, charge / mass, E, dt, eps, max(n))
+    assert rel_l2(fg, gd) <= tol
+    ctx.close()
+
+
+def test_max_rank_cap(oracle_mod):
+    """ParticleData::SetMaxRank (C5: 48^3 at r = 8): ranks never exceed the cap and the capped
+    rounding matches the oracle's."""
+    m = oracle_mod.Mesh.load(mesh_path("fully_periodic_coarse.msh"), [(1, 2), (3, 4), (5, 6)])
+    n, vmin, vmax = (12, 10, 8), [-3.0, -2.0, -2.0], [3.0, 2.0, 2.0]
+    eps, cap, dt = 1e-6, 3, 2e-3
+    f = _initial(m, n, vmin, vmax)
+    E = np.random.default_rng(5).standard_normal((m.nTets, 3))
+    ts = oracle_mod.TuckerSim(m, n, vmin, vmax, 1.0, 1.0, eps, cap)
+    ts.set_pdf(f)
+    ctx, g, _ = _ctx(m, n, vmin, vmax, 1.0, 1.0, {}, eps, cap)
+    ctx.tucker_set_pdf(g, f)
+    ctx.field_set(E)
+    for _ in range(2):
+        ts.update_pdf(dt, E)
+        ctx.step_tucker(g, dt)
+    assert ctx.tucker_ranks(g).max() <= cap
+    assert np.array_equal(ctx.tucker_ranks(g), ts.ranks())
+    # with a binding cap the truncation error is large, and both sides make the same one
+    assert rel_l2(ctx.tucker_get_pdf(g, f.shape[1]), ts.get_pdf()) <= 1e-6
+    ctx.close()
+
+
+def test_uniform_state_is_steady(oracle_mod):
+    """Property: a spatially uniform separable state with E = 0 on a periodic mesh stays put up to
+    the |v.n| rank-6 error times the (vanishing) jump — i.e. exactly, to rounding."""
+    m = oracle_mod.Mesh.load(mesh_path("fully_periodic_coarse.msh"), [(1, 2), (3, 4), (5, 6)])
+    n, vmin, vmax = (16, 8, 8), [-3.0, -1.0, -1.0], [3.0, 1.0, 1.0]
+    _, V = vgrid(n, vmin, vmax)
+    mx = np.exp(-0.5 * (V[0] ** 2 + (V[1] / 0.4) ** 2 + (V[2] / 0.4) ** 2))
+    f = np.tile(mx, (m.nTets, 1))
+    ctx, g, _ = _ctx(m, n, vmin, vmax, 1.0, 1.0, {}, 1e-6)
+    ctx.tucker_set_pdf(g, f)
+    ctx.field_set(np.zeros((m.nTets, 3)))
+    for _ in range(5):
+        ctx.step_tucker(g, 1e-3)
+    assert rel_l2(ctx.tucker_get_pdf(g, f.shape[1]), f) <= 1e-9
+    assert (ctx.tucker_ranks(g) == 1).all()
+    ctx.close()
+
+
+def test_errors(oracle_mod):
+    import vlasovtucker_b200 as vtb
+    m = oracle_mod.Mesh.load(mesh_path("rectangle.msh"), [(3, 4), (5, 6)])
+    ctx = vtb.Context(0)
+    ctx.mesh_upload(tables_from_oracle(m))
+    g = ctx.species_create((8, 4, 4), [-1, -1, -1], [1, 1, 1], 1.0, 1.0)
+    with pytest.raises(RuntimeError, match="Tucker"):
+        ctx.step_tucker(g, 1e-3)                         # not enabled
+    ctx.tucker_enable(g, 1e-6)
+    ctx.tucker_set_pdf(g, np.ones((m.nTets, 128)))
+    ctx.field_set(np.zeros((m.nTets, 3)))
+    with pytest.raises(RuntimeError, match="boundary faces"):
+        ctx.step_tucker(g, 1e-3)                         # x faces have no particle BC yet
+    ctx.close()

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libvt_b200.so")
-SOURCES = ["vt_api.cu", "full_step.cu", "full_step_async.cu", "full_step_tma.cu", "poisson.cu", "halo.cu"]
+SOURCES = ["vt_api.cu", "full_step.cu", "full_step_async.cu", "full_step_tma.cu", "poisson.cu", "halo.cu", "tucker.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--shared", "-cudart", "shared",

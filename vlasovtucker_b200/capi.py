@@ -55,6 +55,13 @@ SIGNATURES = {
     "vt_poisson_solve": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
     "vt_poisson_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), c_dp]),
     "vt_charge_density": (C.c_int, [C.c_void_p, c_ip, C.c_int, c_dp]),
+    "vt_tucker_enable": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "vt_tucker_set_pdf": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "vt_tucker_get_pdf": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "vt_tucker_get_ranks": (C.c_int, [C.c_void_p, C.c_int, c_ip]),
+    "vt_tucker_get_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_ip, c_dp, c_dp, c_dp, c_dp]),
+    "vt_tucker_density": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "vt_step_tucker": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
 }
 
 

@@ -242,3 +242,44 @@ class Context:
         sp = capi.i32(species)
         bg = capi.f64(background)
         capi.check(self.lib.vt_charge_density(self.h, capi.ip(sp), len(sp), capi.dp(bg)))
+
+    # ---- Tucker format (ParticleData<Tucker> / Solver<Tucker>) ----
+    def tucker_enable(self, sp, compr_err=1e-10, max_rank=0):
+        capi.check(self.lib.vt_tucker_enable(self.h, sp, float(compr_err), int(max_rank)))
+        self._tucker_cap = getattr(self, "_tucker_cap", {})
+        self._tucker_cap[sp] = int(max_rank)
+
+    def tucker_set_pdf(self, sp, dense):
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        assert dense.shape[0] == self.nOwned
+        capi.check(self.lib.vt_tucker_set_pdf(self.h, sp, capi.dp(dense)))
+
+    def tucker_get_pdf(self, sp, N):
+        out = np.empty((self.nOwned, N))
+        capi.check(self.lib.vt_tucker_get_pdf(self.h, sp, capi.dp(out)))
+        return out
+
+    def tucker_ranks(self, sp):
+        r = np.empty((self.nOwned, 3), np.int32)
+        capi.check(self.lib.vt_tucker_get_ranks(self.h, sp, capi.ip(r)))
+        return r
+
+    def tucker_factors(self, sp, tet, n):
+        """(core[r0,r1,r2] i0-fastest, [U0,U1,U2] column-major n_k x r_k) of one tet."""
+        r = np.zeros(3, np.int32)
+        core = np.empty(n[0] * n[1] * n[2])
+        us = [np.empty(n[k] * n[k]) for k in range(3)]
+        capi.check(self.lib.vt_tucker_get_factors(self.h, sp, int(tet), capi.ip(r), capi.dp(core), capi.dp(us[0]),
+                                                  capi.dp(us[1]), capi.dp(us[2])))
+        c = core[:r[0] * r[1] * r[2]].reshape(r[2], r[1], r[0]).transpose(2, 1, 0)
+        U = [us[k][:n[k] * r[k]].reshape(r[k], n[k]).T for k in range(3)]
+        return c, U
+
+    def tucker_density(self, sp):
+        d = np.empty(self.nOwned)
+        capi.check(self.lib.vt_tucker_density(self.h, sp, capi.dp(d)))
+        return d
+
+    def step_tucker(self, sp, dt, ext=(0.0, 0.0, 0.0)):
+        ext = capi.f64(ext)
+        capi.check(self.lib.vt_step_tucker(self.h, sp, float(dt), capi.dp(ext)))

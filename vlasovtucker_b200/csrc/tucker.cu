@@ -1,0 +1,715 @@
+// Tucker path on the device — Solver<Tucker>::_UpdatePDF (src/solver.cpp:141-212 with
+// _Flux :314-346, _PDFDerivative<Tucker> :348-361, _PrecomputeNormalTensors :258-293) and the
+// Tucker algebra it calls (src/tucker.cpp: operator+ :190-228, operator* :259-300, scalar
+// :302-316, Compress :66-98 with _ComputeU :442-465).
+//
+// Formulation.  The reference adds and multiplies in Tucker format (ranks grow to r_rhs + 16 r per
+// face) and then rounds: QR of the stacked factors, core transform, truncated HOSVD of the small
+// core.  Because Q is an orthonormal basis of the stacked factors' range, that rounding is exactly
+// the truncated HOSVD of the tensor the sum represents, with the reference's per-singular-value
+// rule (keep sigma_j > eps*|sigma|_2/sqrt(3), at least one, at most maxRank).  For the stacked ranks
+// of this update (R >= n almost immediately) the intermediate is a full n^3 tensor
+// anyway, so this first device implementation evaluates each sum densely in per-CTA scratch and
+// applies the same truncated HOSVD at the same six points per tet-step; the state between steps
+// stays compressed (core r^3 + three n x r factors per tet).  One CTA owns a tet from
+// reconstruction to the re-compressed result.
+//
+//   reconstruct      core x1 U0 x2 U1 x3 U2                               (tucker.cpp:100-104)
+//   hosvd_truncate   per mode: Gram matrix of the unfolding, eigen-decomposition by one-sided
+//                    Jacobi with round-robin parallel ordering (one warp per column pair),
+//                    rank selection, then projection X x_k U_k^T          (tucker.cpp:34-50, 442-465)
+//
+// Accuracy note: singular values come from Gram matrices, so values below ~1e-8 sigma_1 are noise;
+// the rank rule is exact for compression errors >= ~1e-7 (the examples use 1e-6).  For the class
+// default 1e-10 the result is still a valid Tucker approximation within ~1e-8.
+#include "vt_internal.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace vt {
+
+struct TuckerState {
+    int rcap[3];                 // stored rank capacity per mode = min(maxRank, n)
+    size_t coreCap, slot;        // doubles per tet: core, whole slot (core + 3 factors)
+    double* buf[2] = {nullptr, nullptr};   // compressed state, ping-pong
+    int* ranks[2] = {nullptr, nullptr};    // 3 per tet
+    double* vnabs = nullptr;     // rank-<=6 reconstruction of |v.n|, 4 x N per owned tet (solver.cpp:282)
+    double* scratch = nullptr;   // per-CTA dense work space
+    int scratchCTAs = 0;
+    double comprErr = 1e-10;
+    int maxRank = 0;
+    int cur = 0;
+    bool vnabsValid = false;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxN = 64;
+
+struct Dims {
+    int n[3];
+    int N;
+};
+
+// dst (dims with dim[mode] -> rows) = src x_mode M.  M is addressed M[out + ldm*in] (transpose=false,
+// an "rows x n_mode" matrix stored column-major) or M[in + ldm*out] (transpose=true: apply U^T).
+__device__ void mode_apply(const double* __restrict__ src, double* __restrict__ dst, const int din[3], int mode,
+                           const double* __restrict__ M, int ldm, int rowsOut, bool transpose)
+{
+    int dout[3] = {din[0], din[1], din[2]};
+    dout[mode] = rowsOut;
+    const int total = dout[0] * dout[1] * dout[2];
+    const int strideIn = mode == 0 ? 1 : (mode == 1 ? din[0] : din[0] * din[1]);
+    for (int o = threadIdx.x; o < total; o += blockDim.x) {
+        const int o0 = o % dout[0], o1 = (o / dout[0]) % dout[1], o2 = o / (dout[0] * dout[1]);
+        int i[3] = {o0, o1, o2};
+        const int q = i[mode];
+        i[mode] = 0;
+        const int base = i[0] + din[0] * (i[1] + din[1] * i[2]);
+        double s = 0.0;
+        for (int k = 0; k < din[mode]; k++) {
+            const double m = transpose ? M[k + ldm * q] : M[q + ldm * k];
+            s += m * src[base + k * strideIn];
+        }
+        dst[o] = s;
+    }
+    __syncthreads();
+}
+
+// Gram matrix of the mode-k unfolding: G[i + n*j] = sum over the other two indices X(..i..) X(..j..)
+__device__ void gram(const double* __restrict__ X, const int d[3], int mode, double* __restrict__ G)
+{
+    const int n = d[mode];
+    const int a = (mode + 1) % 3, b = (mode + 2) % 3;
+    const int stride[3] = {1, d[0], d[0] * d[1]};
+    for (int p = threadIdx.x; p < n * n; p += blockDim.x) {
+        const int i = p % n, j = p / n;
+        if (j < i) continue;
+        double s = 0.0;
+        for (int ib = 0; ib < d[b]; ib++)
+            for (int ia = 0; ia < d[a]; ia++) {
+                const int off = ia * stride[a] + ib * stride[b];
+                s += X[off + i * stride[mode]] * X[off + j * stride[mode]];
+            }
+        G[i + n * j] = s;
+        G[j + n * i] = s;
+    }
+    __syncthreads();
+}
+
+// Eigen-decomposition of the symmetric PSD n x n matrix in W (column-major, overwritten): one-sided
+// Jacobi W <- W J, V <- V J until the columns of W = G V are orthogonal; eigenvalue_j = |w_j|.
+// Round-robin ordering gives n/2 independent column pairs per round; one warp rotates one pair.
+__device__ void jacobi_eig(double* W, double* V, int n, double* lambda, int* order, int* flag)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int p = threadIdx.x; p < n * n; p += blockDim.x) V[p] = (p % n == p / n) ? 1.0 : 0.0;
+    __syncthreads();
+    const int m = (n + 1) & ~1;   // even number of players; index n (if odd) is a bye
+    for (int sweep = 0; sweep < 40; sweep++) {
+        if (threadIdx.x == 0) *flag = 0;
+        __syncthreads();
+        for (int round = 0; round < m - 1; round++) {
+            for (int pr = warp; pr < m / 2; pr += nwarps) {
+                int p, q;
+                if (pr == 0) {
+                    p = m - 1;
+                    q = round;
+                } else {
+                    p = (round + pr) % (m - 1);
+                    q = (round - pr + (m - 1)) % (m - 1);
+                }
+                if (p >= n || q >= n) continue;
+                if (p > q) {
+                    const int t = p;
+                    p = q;
+                    q = t;
+                }
+                double a = 0, b = 0, g = 0;
+                for (int i = lane; i < n; i += 32) {
+                    const double x = W[i + n * p], y = W[i + n * q];
+                    a += x * x;
+                    b += y * y;
+                    g += x * y;
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    a += __shfl_xor_sync(0xffffffffu, a, o);
+                    b += __shfl_xor_sync(0xffffffffu, b, o);
+                    g += __shfl_xor_sync(0xffffffffu, g, o);
+                }
+                if (g == 0.0 || fabs(g) <= 1e-15 * sqrt(a * b)) continue;
+                if (lane == 0) *flag = 1;
+                const double z = (b - a) / (2 * g);
+                const double t = (z >= 0 ? 1.0 : -1.0) / (fabs(z) + sqrt(1 + z * z));
+                const double cs = 1 / sqrt(1 + t * t), sn = cs * t;
+                for (int i = lane; i < n; i += 32) {
+                    const double x = W[i + n * p], y = W[i + n * q];
+                    W[i + n * p] = cs * x - sn * y;
+                    W[i + n * q] = sn * x + cs * y;
+                    const double vx = V[i + n * p], vy = V[i + n * q];
+                    V[i + n * p] = cs * vx - sn * vy;
+                    V[i + n * q] = sn * vx + cs * vy;
+                }
+            }
+            __syncthreads();
+        }
+        if (*flag == 0) break;
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double s = 0;
+        for (int i = 0; i < n; i++) s += W[i + n * j] * W[i + n * j];
+        lambda[j] = sqrt(s);
+    }
+    __syncthreads();
+    // descending order by rank counting (stable)
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        int rank = 0;
+        for (int i = 0; i < n; i++)
+            if (lambda[i] > lambda[j] || (lambda[i] == lambda[j] && i < j)) rank++;
+        order[rank] = j;
+    }
+    __syncthreads();
+}
+
+struct TruncWork {
+    double* G;        // [kMaxN*kMaxN] shared
+    double* V;        // [kMaxN*kMaxN] shared
+    double* lambda;   // [kMaxN] shared
+    int* order;       // [kMaxN] shared
+    int* flag;        // shared
+    int* rsel;        // [3] shared: selected ranks
+};
+
+// Truncated HOSVD of the dense tensor X (dims d).  Writes the factors to Uout[k] (leading dimension
+// d[k], rcap[k] columns available), the core to coreOut (r0 x r1 x r2 packed), the ranks to rsel.
+// W1/W2 are dense work buffers (>= N doubles each).
+__device__ void hosvd_truncate(const double* X, const int d[3], double eps, int rmax, const int rcap[3], double* const Uout[3],
+                               double* coreOut, double* W1, double* W2, const TruncWork& w)
+{
+    for (int k = 0; k < 3; k++) {
+        const int n = d[k];
+        gram(X, d, k, w.G);
+        jacobi_eig(w.G, w.V, n, w.lambda, w.order, w.flag);
+        if (threadIdx.x == 0) {
+            // sigma_j = sqrt(lambda_j); |sigma|^2 = sum lambda_j              (tucker.cpp:450)
+            double s2 = 0;
+            for (int j = 0; j < n; j++) s2 += w.lambda[j];
+            const double thr = eps * sqrt(s2) / sqrt(3.0);
+            int r = 0;
+            const int cap = min(rmax, rcap[k]);
+            for (int j = 0; j < n; j++) {
+                const double sig = sqrt(fmax(w.lambda[w.order[j]], 0.0));
+                if (r == 0 || (sig > thr && r < cap)) r++;   // sorted: a prefix is kept       (tucker.cpp:454-460)
+                else break;
+            }
+            w.rsel[k] = r;
+        }
+        __syncthreads();
+        const int r = w.rsel[k];
+        for (int p = threadIdx.x; p < n * r; p += blockDim.x) {
+            const int i = p % n, j = p / n;
+            Uout[k][i + n * j] = w.V[i + n * w.order[j]];
+        }
+        __syncthreads();
+    }
+    // core = X x1 U0^T x2 U1^T x3 U2^T
+    int dd[3] = {d[0], d[1], d[2]};
+    mode_apply(X, W1, dd, 0, Uout[0], d[0], w.rsel[0], true);
+    dd[0] = w.rsel[0];
+    mode_apply(W1, W2, dd, 1, Uout[1], d[1], w.rsel[1], true);
+    dd[1] = w.rsel[1];
+    mode_apply(W2, coreOut, dd, 2, Uout[2], d[2], w.rsel[2], true);
+}
+
+// dense = core x1 U0 x2 U1 x3 U2
+__device__ void reconstruct(const double* core, const int r[3], double* const U[3], const int d[3], double* out, double* W1,
+                            double* W2)
+{
+    int dd[3] = {r[0], r[1], r[2]};
+    mode_apply(core, W1, dd, 0, U[0], d[0], d[0], false);
+    dd[0] = d[0];
+    mode_apply(W1, W2, dd, 1, U[1], d[1], d[1], false);
+    dd[1] = d[1];
+    mode_apply(W2, out, dd, 2, U[2], d[2], d[2], false);
+}
+
+struct TuckerParams {
+    int nOwned;
+    int n[3], N;
+    int rcap[3];
+    size_t coreCap, slot;
+    const double* in;      // compressed state at step n
+    const int* rin;
+    double* out;           // compressed state at step n+1
+    int* rout;
+    const TetRec* rec;
+    const double* E;
+    const double* vnabs;   // [nOwned][4][N]
+    double* density;
+    double* wall;
+    double* scratch;       // per CTA: 5 N + 3 kMaxN*kMaxN(U work) doubles
+    size_t scratchPerCTA;
+    double vmin[3], step[3], inv2h[3];
+    double qm, ext[3], dt, wallScale, cellVolume;
+    double eps;
+    int maxRank;
+    const double* denseIn;   // set_pdf path: dense rows to compress (mode 1)
+    double* denseOut;        // get_pdf path: dense rows reconstructed (mode 2)
+    int first;
+    int mode;                // 0 step, 1 compress dense input, 2 reconstruct, 3 |v.n| tables
+    double epsAbs;           // mode 3: compression error for |v.n| (rank cap 6)
+};
+
+__device__ void slot_ptrs(double* base, const TuckerParams& P, double*& core, double* U[3])
+{
+    core = base;
+    U[0] = base + P.coreCap;
+    U[1] = U[0] + (size_t)P.n[0] * P.rcap[0];
+    U[2] = U[1] + (size_t)P.n[1] * P.rcap[1];
+}
+
+__global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
+{
+    extern __shared__ double sDyn[];   // 2 * nmax^2 doubles: Gram matrix and eigenvectors
+    const int nmaxS = max(P.n[0], max(P.n[1], P.n[2]));
+    double* sG = sDyn;
+    double* sV = sDyn + nmaxS * nmaxS;
+    __shared__ double sLambda[kMaxN];
+    __shared__ int sOrder[kMaxN];
+    __shared__ int sFlag;
+    __shared__ int sR[3];
+    __shared__ double sRed[kThreads / 32][5];
+    __shared__ TetRec rec;
+    TruncWork w{sG, sV, sLambda, sOrder, &sFlag, sR};
+
+    const int d[3] = {P.n[0], P.n[1], P.n[2]};
+    const int N = P.N;
+    double* scr = P.scratch + (size_t)blockIdx.x * P.scratchPerCTA;
+    double* A = scr;
+    double* B = A + N;
+    double* RHS = B + N;
+    double* W1 = RHS + N;
+    double* W2 = W1 + N;
+    double* Uw[3] = {W2 + N, W2 + N + (size_t)kMaxN * kMaxN, W2 + N + 2 * (size_t)kMaxN * kMaxN};   // factors of intermediates
+    double* coreW = Uw[2] + (size_t)kMaxN * kMaxN;                                                  // [N]
+    const int fullcap[3] = {d[0], d[1], d[2]};
+
+    for (int t = blockIdx.x; t < P.nOwned; t += gridDim.x) {
+        if (P.mode == 2) {   // reconstruct tet t into denseOut
+            double *core, *U[3];
+            slot_ptrs(const_cast<double*>(P.in) + (size_t)t * P.slot, P, core, U);
+            const int r[3] = {P.rin[3 * t], P.rin[3 * t + 1], P.rin[3 * t + 2]};
+            reconstruct(core, r, U, d, P.denseOut + (size_t)t * N, W1, W2);
+            continue;
+        }
+        if (P.mode == 1) {   // compress dense input into the slot (initial condition: exact, precision 0)
+            double *core, *U[3];
+            slot_ptrs(P.out + (size_t)t * P.slot, P, core, U);
+            for (int e = threadIdx.x; e < N; e += blockDim.x) A[e] = P.denseIn[(size_t)t * N + e];
+            __syncthreads();
+            hosvd_truncate(A, d, 0.0, P.maxRank, P.rcap, U, core, W1, W2, w);
+            if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
+            __syncthreads();
+            continue;
+        }
+        // stage the tet record
+        {
+            const int* g = reinterpret_cast<const int*>(P.rec + t);
+            int* s = reinterpret_cast<int*>(&rec);
+            for (int i = threadIdx.x; i < (int)(sizeof(TetRec) / 4); i += blockDim.x) s[i] = g[i];
+        }
+        __syncthreads();
+        if (P.mode == 3) {   // |v.n| per face, rounded to rank <= 6 (solver.cpp:276-282)
+            for (int f = 0; f < 4; f++) {
+                for (int e = threadIdx.x; e < N; e += blockDim.x) {
+                    const int i0 = e % d[0], i1 = (e / d[0]) % d[1], i2 = e / (d[0] * d[1]);
+                    const double v0 = __dadd_rn(P.vmin[0], __dmul_rn((double)i0, P.step[0]));
+                    const double v1 = __dadd_rn(P.vmin[1], __dmul_rn((double)i1, P.step[1]));
+                    const double v2 = __dadd_rn(P.vmin[2], __dmul_rn((double)i2, P.step[2]));
+                    A[e] = fabs(rec.nrm[f][0] * v0 + rec.nrm[f][1] * v1 + rec.nrm[f][2] * v2);
+                }
+                __syncthreads();
+                hosvd_truncate(A, d, P.epsAbs, 6, fullcap, Uw, coreW, W1, W2, w);
+                const int r[3] = {sR[0], sR[1], sR[2]};
+                reconstruct(coreW, r, Uw, d, const_cast<double*>(P.vnabs) + ((size_t)t * 4 + f) * N, W1, W2);
+            }
+            continue;
+        }
+
+        // ---- mode 0: one explicit step of tet t
+        {
+            double *core, *U[3];
+            slot_ptrs(const_cast<double*>(P.in) + (size_t)t * P.slot, P, core, U);
+            const int r[3] = {P.rin[3 * t], P.rin[3 * t + 1], P.rin[3 * t + 2]};
+            reconstruct(core, r, U, d, A, W1, W2);
+        }
+        for (int e = threadIdx.x; e < N; e += blockDim.x) RHS[e] = 0.0;
+        __syncthreads();
+        double wallAcc[4] = {0, 0, 0, 0};
+        for (int f = 0; f < 4; f++) {
+            const int bc = rec.bc[f];
+            const bool pair = bc == VT_PBC_NONBOUNDARY || bc == VT_PBC_PERIODIC;
+            if (pair) {
+                const int nb = rec.nbr[f];
+                double *core, *U[3];
+                slot_ptrs(const_cast<double*>(P.in) + (size_t)nb * P.slot, P, core, U);
+                const int r[3] = {P.rin[3 * nb], P.rin[3 * nb + 1], P.rin[3 * nb + 2]};
+                reconstruct(core, r, U, d, B, W1, W2);
+            }
+            const double coef = rec.coef[f];
+            const double* va = P.vnabs + ((size_t)t * 4 + f) * N;
+            for (int e = threadIdx.x; e < N; e += blockDim.x) {
+                const int i0 = e % d[0], i1 = (e / d[0]) % d[1], i2 = e / (d[0] * d[1]);
+                const double v0 = __dadd_rn(P.vmin[0], __dmul_rn((double)i0, P.step[0]));
+                const double v1 = __dadd_rn(P.vmin[1], __dmul_rn((double)i1, P.step[1]));
+                const double v2 = __dadd_rn(P.vmin[2], __dmul_rn((double)i2, P.step[2]));
+                const double vn = rec.nrm[f][0] * v0 + rec.nrm[f][1] * v1 + rec.nrm[f][2] * v2;
+                const double a = A[e];
+                double flux;
+                if (pair) flux = 0.5 * (vn * (B[e] + a) - va[e] * (B[e] - a));        // solver.cpp:325-327
+                else if (bc == VT_PBC_ABSORBING) {
+                    flux = 0.5 * (vn * a + va[e] * a);                                // solver.cpp:331-332
+                    if (rec.wallSlot[f] >= 0) wallAcc[f] += flux;
+                } else flux = vn * a;                                                 // Free, solver.cpp:342
+                RHS[e] = RHS[e] - coef * flux;                                        // solver.cpp:168
+            }
+            __syncthreads();
+            // rhs.Compress(comprErr, maxRank)                                           solver.cpp:182
+            hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);
+            const int r[3] = {sR[0], sR[1], sR[2]};
+            reconstruct(coreW, r, Uw, d, RHS, W1, W2);
+        }
+        // acceleration: rhs -= (q/m)(E_k+ext_k) D_k f, D = zero-outside central difference       solver.cpp:187-200, 348-361
+        {
+            double g[3];
+            for (int k = 0; k < 3; k++) g[k] = (P.qm * (P.E[3 * (size_t)t + k] + P.ext[k])) * P.inv2h[k];
+            const int stride[3] = {1, d[0], d[0] * d[1]};
+            for (int e = threadIdx.x; e < N; e += blockDim.x) {
+                const int i[3] = {e % d[0], (e / d[0]) % d[1], e / (d[0] * d[1])};
+                double r = RHS[e];
+                for (int k = 0; k < 3; k++) {
+                    const double up = i[k] + 1 < d[k] ? A[e + stride[k]] : 0.0;
+                    const double dn = i[k] > 0 ? A[e - stride[k]] : 0.0;
+                    r = r - g[k] * (up - dn);
+                }
+                W1[e] = r;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < N; e += blockDim.x) RHS[e] = W1[e];
+            __syncthreads();
+            hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);   // solver.cpp:199
+            const int r[3] = {sR[0], sR[1], sR[2]};
+            reconstruct(coreW, r, Uw, d, RHS, W1, W2);
+        }
+        // pdf += dt*rhs ; pdf.Compress                                                         solver.cpp:207-210
+        for (int e = threadIdx.x; e < N; e += blockDim.x) B[e] = A[e] + P.dt * RHS[e];
+        __syncthreads();
+        {
+            double *core, *U[3];
+            slot_ptrs(P.out + (size_t)t * P.slot, P, core, U);
+            hosvd_truncate(B, d, P.eps, P.maxRank, P.rcap, U, core, W1, W2, w);
+            if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
+            const int r[3] = {sR[0], sR[1], sR[2]};
+            reconstruct(core, r, U, d, B, W1, W2);   // Density() sums the rounded tensor (particle_data.cpp:99)
+        }
+        double acc = 0.0;
+        for (int e = threadIdx.x; e < N; e += blockDim.x) acc += B[e];
+        double vals[5] = {acc, wallAcc[0], wallAcc[1], wallAcc[2], wallAcc[3]};
+        for (int q = 0; q < 5; q++) {
+            double v = vals[q];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot[5] = {0, 0, 0, 0, 0};
+            for (int wv = 0; wv < kThreads / 32; wv++)
+                for (int q = 0; q < 5; q++) tot[q] += sRed[wv][q];
+            P.density[t] = tot[0] * P.cellVolume;
+            for (int f = 0; f < 4; f++)
+                if (rec.wallSlot[f] >= 0) atomicAdd(P.wall + rec.wallSlot[f], P.wallScale * rec.area[f] * tot[1 + f]);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+void tucker_destroy(TuckerState* ts)
+{
+    if (!ts) return;
+    cudaFree(ts->buf[0]);
+    cudaFree(ts->buf[1]);
+    cudaFree(ts->ranks[0]);
+    cudaFree(ts->ranks[1]);
+    cudaFree(ts->vnabs);
+    cudaFree(ts->scratch);
+    delete ts;
+}
+
+namespace {
+
+void fill_params(vt_ctx* ctx, Species& sp, TuckerState& ts, TuckerParams& P)
+{
+    std::memset(&P, 0, sizeof(P));
+    P.nOwned = ctx->nOwned;
+    for (int k = 0; k < 3; k++) {
+        P.n[k] = sp.n[k];
+        P.rcap[k] = ts.rcap[k];
+        P.vmin[k] = sp.vmin[k];
+        P.step[k] = sp.step[k];
+        P.inv2h[k] = 1.0 / (2 * sp.step[k]);
+    }
+    P.N = sp.N;
+    P.coreCap = ts.coreCap;
+    P.slot = ts.slot;
+    P.rec = sp.rec;
+    P.E = ctx->E;
+    P.vnabs = ts.vnabs;
+    P.density = sp.density;
+    P.wall = sp.wall;
+    P.scratch = ts.scratch;
+    P.scratchPerCTA = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
+    P.qm = sp.charge / sp.mass;
+    P.cellVolume = sp.cellVolume;
+    P.eps = ts.comprErr;
+    P.maxRank = ts.maxRank;
+}
+
+void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
+{
+    if (ctx->nOwned == 0) return;
+    const int grid = std::min(ctx->nOwned, ts.scratchCTAs);
+    const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
+    const size_t smem = 2 * (size_t)nmax * nmax * sizeof(double);
+    if (smem > 40 * 1024)
+        VT_CUDA(cudaFuncSetAttribute(k_tucker, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxN * kMaxN * (int)sizeof(double)));
+    k_tucker<<<grid, kThreads, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    VT_CUDA(cudaGetLastError());
+}
+
+TuckerState& state_of(Species& sp)
+{
+    if (!sp.tucker) throw std::runtime_error("species is not in Tucker format (vt_tucker_enable)");
+    return *sp.tucker;
+}
+
+Species& species_of(vt_ctx* ctx, int s)
+{
+    if (s < 0 || s >= (int)ctx->species.size()) throw std::invalid_argument("bad species id");
+    return *ctx->species[s];
+}
+
+template <class F>
+int guard(F f)
+{
+    try {
+        f();
+        return 0;
+    } catch (std::exception& e) {
+        vt_set_error(e.what());
+        return 1;
+    }
+}
+
+void ensure_vnabs(vt_ctx* ctx, Species& sp, TuckerState& ts)
+{
+    if (ts.vnabsValid) return;
+    TuckerParams P;
+    fill_params(ctx, sp, ts, P);
+    P.mode = 3;
+    P.epsAbs = ts.comprErr;
+    launch(ctx, ts, P);
+    ts.vnabsValid = true;
+}
+
+}  // namespace
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" {
+
+int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        if (ctx->nGhost > 0) throw std::runtime_error("the Tucker path is single-GPU for now");
+        for (int k = 0; k < 3; k++)
+            if (sp.n[k] > kMaxN) throw std::runtime_error("Tucker path: velocity grid larger than 64 nodes per axis");
+        if (sp.tucker) tucker_destroy(sp.tucker);
+        TuckerState* ts = new TuckerState();
+        sp.tucker = ts;
+        ts->comprErr = comprErr;
+        const int nmax = std::max({sp.n[0], sp.n[1], sp.n[2]});
+        ts->maxRank = maxRank > 0 ? maxRank : nmax;   // particle_data.cpp:18
+        for (int k = 0; k < 3; k++) ts->rcap[k] = std::min(ts->maxRank, sp.n[k]);
+        ts->coreCap = (size_t)ts->rcap[0] * ts->rcap[1] * ts->rcap[2];
+        ts->slot = ts->coreCap + (size_t)sp.n[0] * ts->rcap[0] + (size_t)sp.n[1] * ts->rcap[1] + (size_t)sp.n[2] * ts->rcap[2];
+        const size_t nA = std::max(1, ctx->nOwned);
+        for (int b = 0; b < 2; b++) {
+            VT_CUDA(cudaMalloc(&ts->buf[b], nA * ts->slot * sizeof(double)));
+            VT_CUDA(cudaMemset(ts->buf[b], 0, nA * ts->slot * sizeof(double)));
+            VT_CUDA(cudaMalloc(&ts->ranks[b], nA * 3 * sizeof(int)));
+            VT_CUDA(cudaMemset(ts->ranks[b], 0, nA * 3 * sizeof(int)));
+        }
+        VT_CUDA(cudaMalloc(&ts->vnabs, nA * 4 * sp.N * sizeof(double)));
+        ts->scratchCTAs = 2 * ctx->prop.multiProcessorCount;
+        const size_t per = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
+        VT_CUDA(cudaMalloc(&ts->scratch, (size_t)ts->scratchCTAs * per * sizeof(double)));
+    });
+}
+
+int vt_tucker_set_pdf(vt_ctx* ctx, int species, const double* dense)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        const size_t bytes = (size_t)ctx->nOwned * sp.N * sizeof(double);
+        double* d = ctx_stage(ctx, bytes);
+        // caller order -> device order row by row
+        for (int p = 0; p < ctx->nOwned; p++)
+            VT_CUDA(cudaMemcpyAsync(d + (size_t)p * sp.N, dense + (size_t)ctx->order[p] * sp.N, (size_t)sp.N * sizeof(double),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+        TuckerParams P;
+        fill_params(ctx, sp, ts, P);
+        P.mode = 1;
+        P.denseIn = d;
+        P.out = ts.buf[ts.cur];
+        P.rout = ts.ranks[ts.cur];
+        launch(ctx, ts, P);
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
+        sp.densityValid = false;
+    });
+}
+
+int vt_tucker_get_pdf(vt_ctx* ctx, int species, double* dense)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        const size_t bytes = (size_t)ctx->nOwned * sp.N * sizeof(double);
+        double* d = ctx_stage(ctx, bytes);
+        TuckerParams P;
+        fill_params(ctx, sp, ts, P);
+        P.mode = 2;
+        P.in = ts.buf[ts.cur];
+        P.rin = ts.ranks[ts.cur];
+        P.denseOut = d;
+        launch(ctx, ts, P);
+        for (int p = 0; p < ctx->nOwned; p++)
+            VT_CUDA(cudaMemcpyAsync(dense + (size_t)ctx->order[p] * sp.N, d + (size_t)p * sp.N, (size_t)sp.N * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int vt_tucker_get_ranks(vt_ctx* ctx, int species, int32_t* ranks)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        std::vector<int> r(3 * (size_t)ctx->nOwned);
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
+        VT_CUDA(cudaMemcpy(r.data(), ts.ranks[ts.cur], r.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int p = 0; p < ctx->nOwned; p++)
+            for (int k = 0; k < 3; k++) ranks[3 * (size_t)ctx->order[p] + k] = r[3 * (size_t)p + k];
+    });
+}
+
+int vt_tucker_get_factors(vt_ctx* ctx, int species, int tet, int32_t ranks[3], double* core, double* u0, double* u1,
+                          double* u2)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        if (tet < 0 || tet >= ctx->nOwned) throw std::out_of_range("tet index");
+        const int p = ctx->inv[tet];
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
+        int r[3];
+        VT_CUDA(cudaMemcpy(r, ts.ranks[ts.cur] + 3 * (size_t)p, sizeof(r), cudaMemcpyDeviceToHost));
+        std::vector<double> slot(ts.slot);
+        VT_CUDA(cudaMemcpy(slot.data(), ts.buf[ts.cur] + (size_t)p * ts.slot, ts.slot * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 3; k++) ranks[k] = r[k];
+        std::memcpy(core, slot.data(), (size_t)r[0] * r[1] * r[2] * sizeof(double));
+        const double* u = slot.data() + ts.coreCap;
+        double* outs[3] = {u0, u1, u2};
+        for (int k = 0; k < 3; k++) {
+            std::memcpy(outs[k], u, (size_t)sp.n[k] * r[k] * sizeof(double));
+            u += (size_t)sp.n[k] * ts.rcap[k];
+        }
+    });
+}
+
+int vt_tucker_density(vt_ctx* ctx, int species, double* density)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        if (!sp.densityValid) {
+            // Sum() of the current tensors: reconstruct and sum (particle_data.cpp:93-102)
+            std::vector<double> dense((size_t)ctx->nOwned * sp.N);
+            // device-side: reuse the reconstruct mode into the stage buffer, then the dense density kernel
+            double* d = ctx_stage(ctx, dense.size() * sizeof(double));
+            TuckerParams P;
+            fill_params(ctx, sp, ts, P);
+            P.mode = 2;
+            P.in = ts.buf[ts.cur];
+            P.rin = ts.ranks[ts.cur];
+            P.denseOut = d;
+            launch(ctx, ts, P);
+            double* keep = sp.f[sp.cur];
+            sp.f[sp.cur] = d;            // launch_density reads sp.f[sp.cur]
+            launch_density(ctx, sp);
+            sp.f[sp.cur] = keep;
+        }
+        if (density) {
+            std::vector<double> tmp(ctx->nOwned);
+            VT_CUDA(cudaStreamSynchronize(ctx->stream));
+            VT_CUDA(cudaMemcpy(tmp.data(), sp.density, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+            for (int p = 0; p < ctx->nOwned; p++) density[ctx->order[p]] = tmp[p];
+        }
+    });
+}
+
+int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        if (sp.danglingFaces > 0)
+            throw std::runtime_error(std::to_string(sp.danglingFaces) + " boundary faces have no neighbour and no particle BC");
+        for (const auto& r : sp.recHost)
+            for (int f = 0; f < 4; f++)
+                if (r.bc[f] == VT_PBC_SOURCE) throw std::runtime_error("Source BC is not implemented on the Tucker path yet");
+        ensure_vnabs(ctx, sp, ts);
+        TuckerParams P;
+        fill_params(ctx, sp, ts, P);
+        P.mode = 0;
+        P.in = ts.buf[ts.cur];
+        P.rin = ts.ranks[ts.cur];
+        P.out = ts.buf[ts.cur ^ 1];
+        P.rout = ts.ranks[ts.cur ^ 1];
+        P.dt = dt;
+        for (int k = 0; k < 3; k++) P.ext[k] = ext ? ext[k] : 0.0;
+        P.wallScale = sp.charge * dt * sp.cellVolume;
+        VT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        launch(ctx, ts, P);
+        VT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        ts.cur ^= 1;
+        sp.densityValid = true;
+    });
+}
+
+}  // extern "C"

@@ -258,6 +258,7 @@ void vt_ctx_destroy(vt_ctx* ctx)
         cudaFree(sp->density);
         cudaFree(sp->densPartial);
         cudaFree(sp->wall);
+        vt::tucker_destroy(sp->tucker);
         delete sp;
     }
     for (void* p : ctx->ipcOpened) cudaIpcCloseMemHandle(p);

@@ -83,9 +83,11 @@ struct Species {
     int nPeers = 0;
     double* peerF[kMaxPeers][2] = {};
     std::vector<int32_t> pushPeer, pushRow;   // 4 per owned tet, caller order, -1 unused
+    struct TuckerState* tucker = nullptr;     // compressed state when the species is in Tucker format
 };
 
 struct PoissonData;
+void tucker_destroy(TuckerState* ts);
 
 }  // namespace vt
 
