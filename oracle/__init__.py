@@ -353,8 +353,14 @@ class TuckerSim:
     def N(self):
         return self.n[0] * self.n[1] * self.n[2]
 
-    def set_particle_bc(self, entity, kind):
-        lib().orc_tsim_set_particle_bc(self.h, int(entity), PBC[kind])
+    def set_particle_bc(self, entity, kind, collect=False, source=None):
+        src = None if source is None else np.ascontiguousarray(source, np.float64)
+        lib().orc_tsim_set_particle_bc_ex(self.h, int(entity), PBC[kind], int(bool(collect)), _d(src))
+
+    def wall_charge(self, entity):
+        L = lib()
+        L.orc_tsim_wall_charge.restype = C.c_double
+        return L.orc_tsim_wall_charge(self.h, int(entity))
 
     def set_pdf(self, f):
         f = np.ascontiguousarray(f, np.float64)

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <stdexcept>
 
@@ -341,6 +342,10 @@ struct TuckerSim {
     Vec3 externalField = {0, 0, 0};
     std::vector<TuckerT> pdf;
     std::vector<int> faceBCType;
+    std::vector<int> faceSource;                // index into `sources` for Source faces
+    std::vector<char> faceCollect;              // ParticleBC::collectCharge
+    std::vector<TuckerT> sources;
+    std::map<int, double> wallCharge;           // entity -> absorbed charge (solver.cpp:171-178)
     std::vector<TuckerT> vNormal, vNormalAbs;   // per face (solver.cpp:258-293)
 
     // particle_data.cpp:23-90: the initial tensors are built with precision 0 (uncompressed ranks)
@@ -384,6 +389,10 @@ struct TuckerSim {
         } else if (bc == PBC_Absorbing) {
             return Scale(0.5, Add(Hadamard(vNormal[fi], A), Hadamard(vNormalAbs[fi], A)));
         }
+        if (bc == PBC_Source) {
+            const TuckerT& B = sources[faceSource[fi]];
+            return Scale(0.5, Sub(Hadamard(vNormal[fi], Add(B, A)), Hadamard(vNormalAbs[fi], Sub(B, A))));
+        }
         return Hadamard(vNormal[fi], A);   // Free
     }
     // solver.cpp:348-361: U_k <- D_k U_k
@@ -408,7 +417,13 @@ struct TuckerSim {
         for (int t = 0; t < nT; t++)
             for (int f = 0; f < 4; f++) {
                 const int fi = 4 * t + f;
-                rhs[t] = Sub(rhs[t], Scale(mesh->faceArea[fi] / mesh->tetVolume[t], Flux(t, f)));
+                const TuckerT flux = Flux(t, f);
+                rhs[t] = Sub(rhs[t], Scale(mesh->faceArea[fi] / mesh->tetVolume[t], flux));
+                if (faceBCType[fi] == PBC_Absorbing && faceCollect[fi]) {
+                    const double dq = charge * (timeStep * mesh->faceArea[fi] * flux.Sum() * vg.cellVolume);
+#pragma omp critical
+                    wallCharge[mesh->faceEntity[fi]] += dq;
+                }
                 rhs[t].Compress(comprErr, maxRank);
             }
 #pragma omp parallel for schedule(dynamic)
@@ -468,6 +483,8 @@ void* orc_tsim_create(void* mesh, const int* n, const double* minV, const double
     s->maxRank = maxRank > 0 ? maxRank : std::max({n[0], n[1], n[2]});   // particle_data.cpp:18
     const size_t nf = s->mesh->facePoints.size();
     s->faceBCType.assign(nf, PBC_NonBoundary);
+    s->faceSource.assign(nf, -1);
+    s->faceCollect.assign(nf, 0);
     for (auto& pr : s->mesh->periodicPairs)
         for (int mark : pr)
             for (size_t i = 0; i < nf; i++)
@@ -480,6 +497,30 @@ void orc_tsim_set_particle_bc(void* h, int entity, int type)
     TuckerSim& s = *(TuckerSim*)h;
     for (size_t i = 0; i < s.mesh->facePoints.size(); i++)
         if (s.mesh->faceEntity[i] == entity) s.faceBCType[i] = type;
+}
+// SetParticleBC with collectCharge / sourcePDF (dense, precision 0); source may be NULL
+void orc_tsim_set_particle_bc_ex(void* h, int entity, int type, int collect, const double* source)
+{
+    TuckerSim& s = *(TuckerSim*)h;
+    int id = -1;
+    if (source) {
+        Ten x(s.vg.n[0], s.vg.n[1], s.vg.n[2]);
+        std::memcpy(x.a.data(), source, (size_t)s.vg.nTotal * 8);
+        s.sources.push_back(TuckerT(x, 0.0, 1000000));
+        id = (int)s.sources.size() - 1;
+    }
+    for (size_t i = 0; i < s.mesh->facePoints.size(); i++)
+        if (s.mesh->faceEntity[i] == entity) {
+            s.faceBCType[i] = type;
+            s.faceCollect[i] = (char)collect;
+            s.faceSource[i] = id;
+        }
+}
+double orc_tsim_wall_charge(void* h, int entity)
+{
+    TuckerSim& s = *(TuckerSim*)h;
+    auto it = s.wallCharge.find(entity);
+    return it == s.wallCharge.end() ? 0.0 : it->second;
 }
 void orc_tsim_set_pdf(void* h, const double* f)
 {

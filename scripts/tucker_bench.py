@@ -4,7 +4,12 @@ import argparse
 import json
 import time
 
+import os
+import sys
+
 import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import vlasovtucker_b200 as vtb
 from vlasovtucker_b200 import synthetic
@@ -43,6 +48,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     a = ap.parse_args()
-    run((7, 7, 7), 11, 1e-6, 0, a.steps)
-    run((7, 7, 7), 32, 1e-6, 8, max(1, a.steps // 2))
+    run((8, 8, 8), 11, 1e-6, 0, a.steps)
+    run((8, 8, 8), 32, 1e-6, 8, max(1, a.steps // 2))
     run((4, 4, 4), 48, 1e-6, 8, max(1, a.steps // 2))

@@ -33,7 +33,33 @@ int main(int argc, char** argv)
     const string which = argv[1], meshFile = argv[2], outFile = argv[4];
     const int iterations = atoi(argv[3]);
     ofstream out(outFile, ios::binary);
-    if (which == "oscillations") {
+    if (which == "oscillations_tucker") {
+        // the same driver with TensorType = Tucker (examples/oscillations.cpp switches by one typedef);
+        // a warm drifting Maxwellian so that the ranks are not trivially 1
+        Mesh mesh(meshFile);
+        mesh.SetPeriodicBounaries({{1, 2}, {3, 4}, {5, 6}});
+        mesh.Reconstruct();
+        VelocityGrid vGrid({11, 9, 7}, {-3, -1, -1}, {3, 1, 1});
+        ParticleData<Tucker> particleData(&mesh, &vGrid);
+        particleData.species = "custom";
+        particleData.mass = 1;
+        particleData.charge = 2.975e-5;
+        MaxwellPDF paramsPDF;
+        double L = 0;
+        for (auto* p : mesh.points) L = max(L, (*p)[0]);
+        auto rhoFunc = [L](const Point& p) { return 10 + 0.2 * sin(p[0] / L * (2 * pi)); };
+        paramsPDF.physDensity = ScalarField(&mesh, rhoFunc);
+        paramsPDF.temperature = 0.3 / boltzConst;
+        paramsPDF.mostProbableV = {0.4, 0, 0};
+        particleData.SetCompressionError(1e-6);
+        particleData.SetMaxwellPDF(paramsPDF);
+        Solver<Tucker> solver(&mesh, &vGrid, &particleData);
+        solver.backgroundChargeDensity = vector<double>(mesh.tets.size(), -particleData.charge * 10);
+        solver.timeStep = 1e-3;
+        solver.nIterations = iterations;
+        solver.Solve();
+        DumpState(out, mesh, particleData);
+    } else if (which == "oscillations") {
         // examples/oscillations.cpp with the stable parameters of SURVEY.md §8d (C1s)
         Mesh mesh(meshFile);
         mesh.SetPeriodicBounaries({{1, 2}, {3, 4}, {5, 6}});

@@ -52,6 +52,36 @@ def test_oscillations_driver(oracle_mod, tmp_path, mesh, iters):
     assert np.abs(vel - s.velocity(sp)).max() <= 1e-8 * max(1e-300, np.abs(s.velocity(sp)).max())
 
 
+def test_oscillations_driver_tucker(oracle_mod, tmp_path):
+    """Solver<Tucker> / ParticleData<Tucker> of the host API (device Tucker path) against the
+    oracle's Tucker algebra + Poisson solver driven in the reference's loop order
+    (solver.cpp:86-139): field from the current density, then _UpdatePDF."""
+    mesh, iters, eps = "fully_periodic_coarse.msh", 6, 1e-6
+    m = oracle_mod.Mesh.load(mesh_path(mesh), [(1, 2), (3, 4), (5, 6)])
+    n, vmin, vmax = (11, 9, 7), [-3, -1, -1], [3, 1, 1]
+    N = 11 * 9 * 7
+    buf = _run("oscillations_tucker", mesh, iters, tmp_path)
+    f, dens, vel, rest = _split(buf, m.nTets, N)
+    assert rest.size == 0
+    q, dt = 2.975e-5, 1e-3
+    L = m.points[:, 0].max()
+    # initial tensors: the Full-format oracle tabulates the same Maxwellian (particle_data.cpp:23-90)
+    s = oracle_mod.Sim(m)
+    sp = s.add_species(n, vmin, vmax, 1.0, q)
+    s.set_maxwell(sp, 10 + 0.2 * np.sin(m.tetCentroid[:, 0] / L * (2 * PI)), 0.3 / 1.38e-23, [0.4, 0.0, 0.0])
+    ts = oracle_mod.TuckerSim(m, n, vmin, vmax, 1.0, q, eps)
+    ts.set_pdf(s.get_pdf(sp))
+    po = oracle_mod.Poisson(m)
+    po.initialize()
+    for _ in range(iters):
+        rho = q * ts.density() - q * 10
+        _, E = po.solve(rho)
+        ts.update_pdf(dt, E)
+    tol = eps + 1e-10
+    assert rel_l2(f, ts.get_pdf()) <= tol
+    assert rel_l2(dens, ts.density()) <= tol
+
+
 def test_sheath_driver(oracle_mod, tmp_path):
     kB, e, me, mi, eV = 1.38e-23, 1.6e-19, 9.1e-31, 1.66e-27, 11604.518
     Te, Ti, dens0 = 1 * eV, 400.0, 1e17

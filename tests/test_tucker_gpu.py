@@ -81,6 +81,61 @@ def test_step_parity(oracle_mod, mesh, pairs, spec, eps):
     ctx.close()
 
 
+def test_source_and_wall_charge(oracle_mod):
+    """Source faces use sourcePDF in the neighbour's place (solver.cpp:335-338); Absorbing faces
+    with collectCharge accumulate charge*dt*area*flux.Sum()*cellVolume (solver.cpp:171-178)."""
+    import vlasovtucker_b200 as vtb
+    m = oracle_mod.Mesh.load(mesh_path("rectangle.msh"), [(3, 4), (5, 6)])
+    n, vmin, vmax = (9, 7, 5), [-3.0, -1.0, -1.0], [3.0, 1.0, 1.0]
+    eps, dt, mass, charge = 1e-6, 2e-3, 2.0, -1.5
+    f = _initial(m, n, vmin, vmax, drift=-0.5)
+    src = 1.3 * _initial(m, n, vmin, vmax, drift=0.8)[0]
+    E = np.random.default_rng(6).standard_normal((m.nTets, 3))
+    spec = {1: ("Absorbing", True), 2: ("Source", False)}
+    ts = oracle_mod.TuckerSim(m, n, vmin, vmax, mass, charge, eps)
+    ts.set_particle_bc(1, "Absorbing", True)
+    ts.set_particle_bc(2, "Source", False, src)
+    ts.set_pdf(f)
+    ctx = vtb.Context(0)
+    ctx.mesh_upload(tables_from_oracle(m))
+    g = ctx.species_create(n, vmin, vmax, mass, charge)
+    bc, col = face_bc_arrays(m, spec)
+    ctx.set_source_pdfs(g, src[None, :])
+    ctx.set_face_bc(g, bc, col, np.where(bc == vtb.PBC["Source"], 0, -1).astype(np.int32))
+    ctx.tucker_enable(g, eps)
+    ctx.tucker_set_pdf(g, f)
+    ctx.field_set(E)
+    for _ in range(3):
+        ts.update_pdf(dt, E)
+        ctx.step_tucker(g, dt)
+    tol = eps + 1e-10
+    assert rel_l2(ctx.tucker_get_pdf(g, f.shape[1]), ts.get_pdf()) <= tol
+    qo, qg = ts.wall_charge(1), ctx.wall_charge(g, 1)
+    assert qo != 0.0 and abs(qg - qo) <= tol * abs(qo)
+    ctx.close()
+
+
+def test_generic_entry_points_on_tucker_species(oracle_mod):
+    """vt_species_set_maxwell / density / velocity / get_pdf serve a Tucker species too
+    (ParticleData<Tucker>::SetMaxwellPDF, Density, Velocity — particle_data.cpp:23-128)."""
+    m = oracle_mod.Mesh.load(mesh_path("fully_periodic_coarse.msh"), [(1, 2), (3, 4), (5, 6)])
+    n, vmin, vmax = (10, 8, 6), [-3.0, -2.0, -2.0], [3.0, 2.0, 2.0]
+    dens = 1e3 * (1 + 0.2 * np.cos(m.tetCentroid[:, 1]))
+    s = oracle_mod.Sim(m)
+    sp = s.add_species(n, vmin, vmax, 9.1e-31, 1.0)
+    T = 0.4 * 9.1e-31 / 1.38e-23
+    s.set_maxwell(sp, dens, T, [0.3, 0.0, -0.2])
+    ctx, g, _ = _ctx(m, n, vmin, vmax, 9.1e-31, 1.0, {}, 1e-6)
+    ctx.set_maxwell(g, dens, T, [0.3, 0.0, -0.2])
+    assert rel_l2(ctx.get_pdf(g), s.get_pdf(sp)) <= 1e-12
+    assert rel_l2(ctx.density(g), s.density(sp)) <= 1e-12
+    assert np.abs(ctx.velocity(g) - s.velocity(sp)).max() <= 1e-10
+    ctx.tucker_enable(g, 1e-6, 3)                        # re-configuration keeps the state
+    assert ctx.tucker_ranks(g).max() <= 3
+    assert rel_l2(ctx.get_pdf(g), s.get_pdf(sp)) <= 1e-9  # a Maxwellian has rank (1,1,1)
+    ctx.close()
+
+
 def test_max_rank_cap(oracle_mod):
     """ParticleData::SetMaxRank (C5: 48^3 at r = 8): ranks never exceed the cap and the capped
     rounding matches the oracle's."""

@@ -335,6 +335,7 @@ bool launch_full_step_async(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind
 void launch_density(vt_ctx* ctx, Species& sp)
 {
     if (ctx->nOwned == 0) return;
+    if (sp.tucker) tucker_materialize(ctx, sp);
     k_density_full<<<ctx->nOwned, 256, 0, ctx->stream>>>(sp.f[sp.cur], sp.density, sp.N, sp.cellVolume);
     ctx->launches++;
     VT_CUDA(cudaGetLastError());
@@ -384,7 +385,9 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
     p.wallScale = sp.charge * dt * sp.cellVolume;
     for (int i = 0; i < kMaxPeers; i++) p.peerFn[i] = i < sp.nPeers ? sp.peerF[i][sp.cur ^ 1] : nullptr;
 
-    const size_t need = (size_t)ctx->nOwned * p.nChunks;
+    p.densSplit = 1;
+    const size_t need = (size_t)ctx->nOwned * p.nChunks * ((ctx->variant & 16) ? 8 : 1);
+    if (need > 2147483647ULL) throw std::runtime_error("vt_step_full: too many density partial sums");
     if ((size_t)sp.densPartialCap < need) {
         if (sp.densPartial) VT_CUDA(cudaFree(sp.densPartial));
         sp.densPartial = nullptr;
@@ -446,7 +449,7 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
     VT_CUDA(cudaGetLastError());
 
     k_density_reduce<<<(ctx->nOwned + 255) / 256, 256, 0, ctx->stream>>>(sp.densPartial, sp.density, ctx->nOwned,
-                                                                        p.nChunks, sp.cellVolume);
+                                                                        p.nChunks * p.densSplit, sp.cellVolume);
     ctx->launches++;
     VT_CUDA(cudaGetLastError());
     sp.cur ^= 1;

@@ -1,28 +1,40 @@
-// K1 (TMA variant) — the fused full-format kinetic update as a persistent, bulk-async-copy
-// pipelined kernel for sm_100a.  Same arithmetic and same results as full_step.cu (which stays
-// as the general path for velocity grids this layout does not cover); see that file for the
-// reference citations of each term.
+// K1 (bulk-copy pipeline) — the fused full-format kinetic update as a persistent, warp-specialised
+// kernel for sm_100a.  Same arithmetic and same results as full_step.cu (which stays as the
+// general path for velocity grids this layout does not cover); see that file for the reference
+// citations of each term.
 //
-// Why: the register-staged kernel is latency bound — ~120 registers per thread cap it at 16
-// warps per SM, each with nine 512-byte loads in flight, which covers only about a third of
-// HBM's bandwidth-latency product (profiles/round1_notes.md).  Here the loads are issued by one
-// thread per CTA as bulk async copies (cp.async.bulk, the 1-D TMA path; SASS UBLKCP) into a
-// shared-memory ring, completion is tracked by mbarriers, and no register is tied up by data
-// in flight: two to three complete plane sets (own plane + 4 neighbour planes, 40 KiB each at
-// 32x32) are always on their way while the 512 threads compute from shared memory.
+// Why: the register-staged kernel is latency bound — 128 registers per thread cap it at 16 warps
+// per SM and every byte in flight is held by a register (profiles/r1_k_full_step_summary.json:
+// 73 % of stall samples are long-scoreboard).  Here one producer warp per CTA issues the loads as
+// bulk async copies (cp.async.bulk, the 1-D TMA path; SASS UBLKCP) of whole velocity planes
+// (n0*n1 doubles, 8 KiB at 32x32) into shared-memory rings; completion is tracked by mbarriers
+// ("full"), consumer warps hand slots back through a second set ("empty"), and no register is
+// tied up by data in flight: ~150 KiB per SM are permanently on their way while eight consumer
+// warps compute from shared memory.  There is no CTA-wide barrier in the steady state.
 //
-// Work: one CTA per SM, persistent; work items (tet, chunk of i2-planes) are dealt round-robin
-// in the same brick-major order as the general kernel, so the CTAs in flight still share an L2
-// working set.  A thread owns KPT fixed (i0-pair, i1) columns of the plane and marches along
+// Work: one CTA per SM, persistent.  Work items (tet, chunk of i2-planes) are handed out through a
+// global atomic queue in brick-major, chunk, tet order, so that at any moment all SMs work on the
+// same few hundred tets and the same i2 window — the neighbour rows another CTA needs are then in
+// L2 (the static round-robin of the first version of this file measured 3.1x the algorithmic DRAM
+// traffic).  A consumer thread owns KPT fixed (i0-pair, i1) columns of the plane and marches along
 // i2 keeping the own-row values prev/cur/next in registers; the i0 and i1 stencil neighbours and
 // the four neighbour tets' values come from shared memory.
+//
+// Stage stream of one item with npl planes starting at pl0 (periodic in i2, solver.cpp:380-389):
+//   own stage s = 0 .. npl+1  : plane pl0-1+s of the tet's own row          (ring of OD planes)
+//   nbr stage j = 0 .. npl-1  : plane pl0+j of the (up to) four neighbours  (ring of S x 4 planes)
+// The producer issues own(0), own(1), nbr(0), own(2), nbr(1), ...; computing plane j needs
+// own(j+1) [centre, i0/i1 neighbours], own(j+2) [i2+1], nbr(j), and prev/cur from registers.
 #include "vt_internal.h"
 
 namespace vt {
 
 namespace {
 
-constexpr int kOwnRing = 4;
+constexpr int kConsWarps = 8;
+constexpr int kConsThreads = kConsWarps * 32;
+constexpr int kItemRing = 4;
+constexpr int kMaxRing = 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -33,6 +45,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
@@ -68,11 +84,13 @@ __device__ __forceinline__ bool is_pair(int bc)
     return bc == VT_PBC_NONBOUNDARY || bc == VT_PBC_PERIODIC || bc == VT_PBC_SOURCE;
 }
 
-struct Item {
-    int tet, chunk, pl0, npl;
+struct ItemHdr {
+    int tet, chunk, pl0, npl;   // tet < 0: no more work
+    double E[3];                // field of the tet, fetched by the producer one item ahead
+    double pad;
 };
 
-__device__ __forceinline__ bool decode_item(const StepParams& p, long long w, long long total, Item& it)
+__device__ __forceinline__ bool decode_item(const StepParams& p, long long w, long long total, ItemHdr& it)
 {
     if (w >= total) return false;
     const int perBrick = p.brickTets * p.nChunks;
@@ -87,95 +105,133 @@ __device__ __forceinline__ bool decode_item(const StepParams& p, long long w, lo
     return true;
 }
 
-struct TmaParams {
+struct BulkParams {
     StepParams s;
-    int S;            // neighbour ring depth
+    int OD, S;        // own ring depth (planes), neighbour ring depth (4-plane sets)
     int planeElems;   // n0*n1
     int PV;           // double2 per plane
+    unsigned long long* queue;
+    long long total;
 };
 
 struct Smem {
-    double* ownRing;     // [kOwnRing][PE]
+    double* ownRing;     // [OD][PE]
     double* nbrRing;     // [S][4][PE]
-    uint64_t* barOwn;    // [kOwnRing]
-    uint64_t* barNbr;    // [S]
-    TetRec* rec;         // [2]
-    double* tz;          // [2][n2][4]
-    double* red;         // [16][5]
+    TetRec* rec;         // [kItemRing]
+    ItemHdr* hdr;        // [kItemRing]
+    uint64_t *ownFull, *ownEmpty, *nbrFull, *nbrEmpty, *itemFull, *itemEmpty;
 };
 
-// Producer cursor: which stage of which item is issued next, and how far both rings are filled.
-struct Producer {
-    long long pw;        // work index of the item being issued
-    int pk;              // its ordinal in this CTA's sequence
-    int ps;              // next stage of that item (0 .. npl+1)
-    Item it;
-    unsigned ownIssued, nbrIssued, ownFreed, nbrFreed;
+// position in a ring of D slots; `phase` flips at every wrap (mbarrier parity of the slot's use)
+struct Cursor {
+    int slot = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int D)
+    {
+        if (++slot == D) {
+            slot = 0;
+            phase ^= 1u;
+        }
+    }
 };
 
-// Issue stages in stream order while both rings have room; never run past item kConsumer+1
-// (only two tet records are resident).  Stage s of an item carries own plane pl0-1+s and, for
-// 1 <= s <= npl, the four neighbour planes pl0+s-1.
-__device__ __noinline__ void produce(const TmaParams& P, const Smem& sm, Producer& pr, int kConsumer, long long total)
+// ---- producer: one thread; claims items from the queue and keeps both rings full
+__device__ void producer_loop(const BulkParams& P, const Smem& sm)
 {
     const StepParams& p = P.s;
     const int PE = P.planeElems;
     const uint32_t PB = (uint32_t)PE * 8u;
-    while (pr.pw < total && pr.pk <= kConsumer + 1) {
-        const bool needNbr = pr.ps >= 1 && pr.ps <= pr.it.npl;
-        if (pr.ownIssued - pr.ownFreed >= (unsigned)kOwnRing) break;
-        if (needNbr && pr.nbrIssued - pr.nbrFreed >= (unsigned)P.S) break;
-        const TetRec& r = sm.rec[pr.pk & 1];
-        int ip = pr.it.pl0 - 1 + pr.ps;                  // periodic in v2 (solver.cpp:380-389)
-        if (ip < 0) ip += p.n2;
-        if (ip >= p.n2) ip -= p.n2;
-        {
-            const unsigned slot = pr.ownIssued % kOwnRing;
-            mbar_expect_tx(sm.barOwn + slot, PB);
-            bulk_g2s(sm.ownRing + (size_t)slot * PE, p.f + (size_t)pr.it.tet * p.N + (size_t)ip * PE, PB, sm.barOwn + slot);
-            pr.ownIssued++;
+    Cursor cItem, cPost, cOwn, cNbr;
+
+    // An item slot completes on two arrivals: the record's bulk copy (posted here) and the field
+    // values, which the producer loads into registers here and stores one iteration later
+    // (finish_item) so that their latency is never waited for.
+    double ePend[3] = {0.0, 0.0, 0.0};
+    int pendSlot = -1;
+    auto post_item = [&](long long w) {   // header + tet record of the item into slot cPost
+        mbar_wait(sm.itemEmpty + cPost.slot, cPost.phase ^ 1u);
+        ItemHdr h;
+        if (decode_item(p, w, P.total, h)) {
+            sm.hdr[cPost.slot].tet = h.tet;
+            sm.hdr[cPost.slot].chunk = h.chunk;
+            sm.hdr[cPost.slot].pl0 = h.pl0;
+            sm.hdr[cPost.slot].npl = h.npl;
+#pragma unroll
+            for (int q = 0; q < 3; q++) ePend[q] = __ldg(p.E + 3 * (size_t)h.tet + q);
+            mbar_expect_tx(sm.itemFull + cPost.slot, (uint32_t)sizeof(TetRec));
+            bulk_g2s(sm.rec + cPost.slot, p.rec + h.tet, (uint32_t)sizeof(TetRec), sm.itemFull + cPost.slot);
+        } else {
+            sm.hdr[cPost.slot].tet = -1;
+            mbar_arrive(sm.itemFull + cPost.slot);
         }
-        if (needNbr) {
-            const unsigned slot = pr.nbrIssued % P.S;
-            uint64_t* bar = sm.barNbr + slot;
-            int cnt = 0;
-            for (int f = 0; f < 4; f++) cnt += is_pair(r.bc[f]) ? 1 : 0;
-            mbar_expect_tx(bar, PB * cnt);
-            const int plane = pr.it.pl0 + pr.ps - 1;
-            for (int f = 0; f < 4; f++) {
-                if (!is_pair(r.bc[f])) continue;
+        pendSlot = cPost.slot;
+        cPost.advance(kItemRing);
+    };
+    auto finish_item = [&]() {
+#pragma unroll
+        for (int q = 0; q < 3; q++) sm.hdr[pendSlot].E[q] = ePend[q];
+        mbar_arrive(sm.itemFull + pendSlot);
+    };
+
+    long long wNext = (long long)atomicAdd(P.queue, 1ULL);
+    post_item(wNext);
+    wNext = (long long)atomicAdd(P.queue, 1ULL);
+    while (true) {
+        finish_item();                                      // item k
+        post_item(wNext);                                   // item k+1: its record lands while item k streams
+        wNext = (long long)atomicAdd(P.queue, 1ULL);        // item k+2: the ticket is used one iteration later
+        mbar_wait(sm.itemFull + cItem.slot, cItem.phase);
+        const ItemHdr h = sm.hdr[cItem.slot];
+        if (h.tet < 0) break;
+        const TetRec& r = sm.rec[cItem.slot];
+        const double* rows[4];
+        int cnt = 0;
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            rows[f] = nullptr;
+            if (is_pair(r.bc[f])) {
                 const int n = r.nbr[f];
-                const double* row = n >= 0 ? p.f + (size_t)n * p.N : p.src + (size_t)(-2 - n) * p.N;
-                bulk_g2s(sm.nbrRing + ((size_t)slot * 4 + f) * PE, row + (size_t)plane * PE, PB, bar);
+                rows[f] = n >= 0 ? p.f + (size_t)n * p.N : p.src + (size_t)(-2 - n) * p.N;
+                cnt++;
             }
-            pr.nbrIssued++;
         }
-        pr.ps++;
-        if (pr.ps > pr.it.npl + 1) {
-            pr.pw += gridDim.x;
-            pr.pk++;
-            pr.ps = 0;
-            if (pr.pw < total) decode_item(p, pr.pw, total, pr.it);
+        const double* own = p.f + (size_t)h.tet * p.N;
+        for (int s = 0; s <= h.npl + 1; s++) {
+            int ip = h.pl0 - 1 + s;
+            if (ip < 0) ip += p.n2;
+            if (ip >= p.n2) ip -= p.n2;
+            mbar_wait(sm.ownEmpty + cOwn.slot, cOwn.phase ^ 1u);
+            mbar_expect_tx(sm.ownFull + cOwn.slot, PB);
+            bulk_g2s(sm.ownRing + (size_t)cOwn.slot * PE, own + (size_t)ip * PE, PB, sm.ownFull + cOwn.slot);
+            cOwn.advance(P.OD);
+            if (s >= 1 && s <= h.npl) {
+                const size_t plane = (size_t)(h.pl0 + s - 1) * PE;
+                uint64_t* bar = sm.nbrFull + cNbr.slot;
+                mbar_wait(sm.nbrEmpty + cNbr.slot, cNbr.phase ^ 1u);
+                if (cnt > 0) mbar_expect_tx(bar, PB * cnt);
+                else mbar_arrive(bar);
+#pragma unroll
+                for (int f = 0; f < 4; f++)
+                    if (rows[f]) bulk_g2s(sm.nbrRing + ((size_t)cNbr.slot * 4 + f) * PE, rows[f] + plane, PB, bar);
+                cNbr.advance(P.S);
+            }
         }
+        cItem.advance(kItemRing);
     }
 }
 
-// All planes of one work item.  GENERIC: per-face boundary conditions and halo push (branches
-// are uniform across the CTA); otherwise four pair faces and no push.
+// ---- consumers: all planes of one work item.  GENERIC: per-face boundary conditions and halo
+// push (branches are uniform across the CTA); otherwise four pair faces and no push.
 template <int KPT, bool UPWIND, bool GENERIC>
-__device__ __forceinline__ void item_compute(const TmaParams& P, const Smem& sm, Producer& pr, const Item& cur,
-                                             const int k, const unsigned ownBase, const unsigned nbrBase,
-                                             const long long total, const int (&colV)[KPT], const int (&colI0)[KPT],
-                                             const int (&colI1)[KPT], const bool (&colOn)[KPT], double& accDens,
-                                             double (&accWall)[4])
+__device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm, const ItemHdr& cur, const TetRec& rec,
+                                             Cursor& cOwn, Cursor& cNbr, const int (&colV)[KPT], const int (&colI0)[KPT],
+                                             const int (&colI1)[KPT], const bool (&colOn)[KPT])
 {
     const StepParams& p = P.s;
     const int PE = P.planeElems;
-    const int tid = threadIdx.x;
-    const TetRec& rec = sm.rec[k & 1];
-    const double* tzk = sm.tz + (size_t)(k & 1) * 4 * p.n2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    double cxy[KPT][4][2], hc[4];
+    double cxy[KPT][4][2], hc[4], cz[4];
     bool pairF[4], absF[4], colF[4];
 #pragma unroll
     for (int f = 0; f < 4; f++) {
@@ -185,6 +241,7 @@ __device__ __forceinline__ void item_compute(const TmaParams& P, const Smem& sm,
         colF[f] = GENERIC && rec.wallSlot[f] >= 0;
         hc[f] = pairF[f] ? 0.5 * rec.coef[f] : rec.coef[f];
         const double pre = (UPWIND && pairF[f]) ? rec.coef[f] : 1.0;
+        cz[f] = pre;
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
             const double v1 = __dadd_rn(p.vmin[1], __dmul_rn((double)colI1[kk], p.step[1]));
@@ -197,7 +254,7 @@ __device__ __forceinline__ void item_compute(const TmaParams& P, const Smem& sm,
     }
     double g[3];
 #pragma unroll
-    for (int q = 0; q < 3; q++) g[q] = (p.qm * (p.E[3 * (size_t)cur.tet + q] + p.ext[q])) * p.inv2h[q];
+    for (int q = 0; q < 3; q++) g[q] = (p.qm * (cur.E[q] + p.ext[q])) * p.inv2h[q];
     double* nrow = p.fn + (size_t)cur.tet * p.N;
     double* push[4] = {nullptr, nullptr, nullptr, nullptr};
     if (GENERIC) {
@@ -205,30 +262,41 @@ __device__ __forceinline__ void item_compute(const TmaParams& P, const Smem& sm,
         for (int q = 0; q < 4; q++)
             if (rec.pushPeer[q] >= 0) push[q] = p.peerFn[rec.pushPeer[q]] + (size_t)rec.pushRow[q] * p.N;
     }
+    double accDens = 0.0;
+    double accWall[4] = {0.0, 0.0, 0.0, 0.0};
 
-    // first two own stages: prev, cur
+    // own stages 0 and 1: prev (registers only) and cur (registers + i0/i1 neighbours from smem)
     double2 prv[KPT], cr[KPT];
+    mbar_wait(sm.ownFull + cOwn.slot, cOwn.phase);
     {
-        const unsigned g0 = ownBase, g1 = ownBase + 1;
-        mbar_wait(sm.barOwn + (g0 % kOwnRing), (g0 / kOwnRing) & 1);
-        mbar_wait(sm.barOwn + (g1 % kOwnRing), (g1 / kOwnRing) & 1);
-        const double* s0 = sm.ownRing + (size_t)(g0 % kOwnRing) * PE;
-        const double* s1 = sm.ownRing + (size_t)(g1 % kOwnRing) * PE;
+        const double* s0 = sm.ownRing + (size_t)cOwn.slot * PE;
 #pragma unroll
-        for (int kk = 0; kk < KPT; kk++) {
-            prv[kk] = *reinterpret_cast<const double2*>(s0 + 2 * colV[kk]);
-            cr[kk] = *reinterpret_cast<const double2*>(s1 + 2 * colV[kk]);
-        }
+        for (int kk = 0; kk < KPT; kk++) prv[kk] = *reinterpret_cast<const double2*>(s0 + 2 * colV[kk]);
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sm.ownEmpty + cOwn.slot);
+    cOwn.advance(P.OD);
+    mbar_wait(sm.ownFull + cOwn.slot, cOwn.phase);
+    const double* sc = sm.ownRing + (size_t)cOwn.slot * PE;
+    int scSlot = cOwn.slot;
+    cOwn.advance(P.OD);
+#pragma unroll
+    for (int kk = 0; kk < KPT; kk++) cr[kk] = *reinterpret_cast<const double2*>(sc + 2 * colV[kk]);
 
     for (int j = 0; j < cur.npl; j++) {
-        const unsigned gc = ownBase + j + 1, gn = ownBase + j + 2, cn = nbrBase + j;
-        mbar_wait(sm.barOwn + (gn % kOwnRing), (gn / kOwnRing) & 1);
-        mbar_wait(sm.barNbr + (cn % P.S), (cn / P.S) & 1);
-        const double* sc = sm.ownRing + (size_t)(gc % kOwnRing) * PE;       // plane j: i0/i1 neighbours
-        const double* sn = sm.ownRing + (size_t)(gn % kOwnRing) * PE;       // plane j+1
-        const double* sb = sm.nbrRing + (size_t)(cn % P.S) * 4 * PE;
-        const double tzf[4] = {tzk[4 * j], tzk[4 * j + 1], tzk[4 * j + 2], tzk[4 * j + 3]};
+        mbar_wait(sm.ownFull + cOwn.slot, cOwn.phase);
+        const double* sn = sm.ownRing + (size_t)cOwn.slot * PE;       // plane j+1
+        const int snSlot = cOwn.slot;
+        cOwn.advance(P.OD);
+        mbar_wait(sm.nbrFull + cNbr.slot, cNbr.phase);
+        const double* sb = sm.nbrRing + (size_t)cNbr.slot * 4 * PE;
+        const int nbSlot = cNbr.slot;
+        cNbr.advance(P.S);
+
+        const double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + j), p.step[2]));
+        double tzf[4];
+#pragma unroll
+        for (int f = 0; f < 4; f++) tzf[f] = cz[f] * (rec.nrm[f][2] * v2);
         const size_t gplane = (size_t)(cur.pl0 + j) * PE;
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
@@ -290,193 +358,150 @@ __device__ __forceinline__ void item_compute(const TmaParams& P, const Smem& sm,
             prv[kk] = cr[kk];
             cr[kk] = nx;
         }
-        __syncthreads();   // every thread is done with own stage gc and neighbour slot cn
-        if (tid == 0) {
-            pr.ownFreed = ownBase + ((j == cur.npl - 1) ? cur.npl + 2 : j + 2);
-            pr.nbrFreed = nbrBase + j + 1;
-            produce(P, sm, pr, k, total);
+        __syncwarp();   // every lane is done with own stage sc and neighbour slot nbSlot
+        if (lane == 0) {
+            mbar_arrive(sm.ownEmpty + scSlot);
+            mbar_arrive(sm.nbrEmpty + nbSlot);
+        }
+        sc = sn;
+        scSlot = snSlot;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sm.ownEmpty + scSlot);   // the last own stage (plane pl0+npl)
+
+    // ---- item epilogue: sum_v f' (Density) per warp, reduced in fixed order by k_density_reduce;
+    // absorbed flux (wall charge)
+    const double sd = warp_sum(accDens);
+    if (lane == 0) p.densPartial[((size_t)cur.tet * p.nChunks + cur.chunk) * kConsWarps + warp] = sd;
+    if (GENERIC) {
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            if (!colF[f]) continue;
+            const double wv = warp_sum(accWall[f]);
+            // charge * (timeStep * area * flux.Sum() * cellVolume), solver.cpp:173-177
+            if (lane == 0) atomicAdd(p.wall + rec.wallSlot[f], p.wallScale * rec.area[f] * wv);
         }
     }
 }
 
 template <int KPT, bool UPWIND>
-__global__ void __launch_bounds__(512, 1) k_full_step_tma(const TmaParams P)
+__global__ void __launch_bounds__(kConsThreads + 32, 1) k_full_step_bulk(const BulkParams P)
 {
     const StepParams& p = P.s;
     extern __shared__ __align__(128) unsigned char smraw[];
     const int PE = P.planeElems;
     Smem sm;
     sm.ownRing = reinterpret_cast<double*>(smraw);
-    sm.nbrRing = sm.ownRing + (size_t)kOwnRing * PE;
-    sm.barOwn = reinterpret_cast<uint64_t*>(sm.nbrRing + (size_t)P.S * 4 * PE);
-    sm.barNbr = sm.barOwn + kOwnRing;
-    sm.rec = reinterpret_cast<TetRec*>(sm.barNbr + 8);
-    sm.tz = reinterpret_cast<double*>(sm.rec + 2);
-    sm.red = sm.tz + 2 * 4 * p.n2;
+    sm.nbrRing = sm.ownRing + (size_t)P.OD * PE;
+    sm.rec = reinterpret_cast<TetRec*>(sm.nbrRing + (size_t)P.S * 4 * PE);
+    sm.hdr = reinterpret_cast<ItemHdr*>(sm.rec + kItemRing);
+    sm.ownFull = reinterpret_cast<uint64_t*>(sm.hdr + kItemRing);
+    sm.ownEmpty = sm.ownFull + kMaxRing;
+    sm.nbrFull = sm.ownEmpty + kMaxRing;
+    sm.nbrEmpty = sm.nbrFull + kMaxRing;
+    sm.itemFull = sm.nbrEmpty + kMaxRing;
+    sm.itemEmpty = sm.itemFull + kItemRing;
 
     const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
-    const long long total = (long long)p.nOwned * p.nChunks;
-    const int G = gridDim.x;
+    if (tid == 0) {
+        for (int i = 0; i < P.OD; i++) {
+            mbar_init(sm.ownFull + i, 1);
+            mbar_init(sm.ownEmpty + i, kConsWarps);
+        }
+        for (int i = 0; i < P.S; i++) {
+            mbar_init(sm.nbrFull + i, 1);
+            mbar_init(sm.nbrEmpty + i, kConsWarps);
+        }
+        for (int i = 0; i < kItemRing; i++) {
+            mbar_init(sm.itemFull + i, 2);
+            mbar_init(sm.itemEmpty + i, kConsWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    // fixed columns of this thread
+    if (tid >= kConsThreads) {
+        if (tid == kConsThreads) producer_loop(P, sm);
+        return;
+    }
+
+    // fixed columns of this consumer thread
     int colV[KPT], colI0[KPT], colI1[KPT];
     bool colOn[KPT];
 #pragma unroll
     for (int kk = 0; kk < KPT; kk++) {
-        const int v = tid + kk * nthr;
+        const int v = tid + kk * kConsThreads;
         colOn[kk] = v < P.PV;
         colV[kk] = colOn[kk] ? v : 0;
         colI0[kk] = (colV[kk] % p.nvec0) * 2;
         colI1[kk] = colV[kk] / p.nvec0;
     }
-
-    if (tid == 0) {
-        for (int i = 0; i < kOwnRing; i++) mbar_init(sm.barOwn + i, 1);
-        for (int i = 0; i < P.S; i++) mbar_init(sm.barNbr + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    Item cur, nxt;
-    const bool haveCur = decode_item(p, blockIdx.x, total, cur);
-    bool haveNxt = decode_item(p, (long long)blockIdx.x + G, total, nxt);
-    auto load_rec = [&](int slot, int tet) {
-        const int* gsrc = reinterpret_cast<const int*>(p.rec + tet);
-        int* s = reinterpret_cast<int*>(sm.rec + slot);
-        for (int i = tid; i < (int)(sizeof(TetRec) / 4); i += nthr) s[i] = gsrc[i];
-    };
-    if (haveCur) load_rec(0, cur.tet);
-    if (haveNxt) load_rec(1, nxt.tet);
-    __syncthreads();
-    if (!haveCur) return;
-
-    Producer pr;
-    pr.pw = blockIdx.x;
-    pr.pk = 0;
-    pr.ps = 0;
-    pr.it = cur;
-    pr.ownIssued = pr.nbrIssued = pr.ownFreed = pr.nbrFreed = 0;
-    if (tid == 0) produce(P, sm, pr, 0, total);
-
-    unsigned ownBase = 0, nbrBase = 0;   // global stage / compute counters at the start of the item
-    int k = 0;
-    long long w = blockIdx.x;
+    Cursor cItem, cOwn, cNbr;
+    const int lane = tid & 31;
     while (true) {
-        const TetRec& rec = sm.rec[k & 1];
-        // per-plane part of v.n for this item: (A/V) n_z v2(i2)
-        double* tzk = sm.tz + (size_t)(k & 1) * 4 * p.n2;
-        for (int i = tid; i < 4 * cur.npl; i += nthr) {
-            const int f = i & 3, pl = i >> 2;
-            const double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + pl), p.step[2]));
-            const double pre = (UPWIND && is_pair(rec.bc[f])) ? rec.coef[f] : 1.0;
-            tzk[4 * pl + f] = pre * (rec.nrm[f][2] * v2);
-        }
-        __syncthreads();
+        mbar_wait(sm.itemFull + cItem.slot, cItem.phase);
+        const ItemHdr cur = sm.hdr[cItem.slot];
+        if (cur.tet < 0) break;
+        const TetRec& rec = sm.rec[cItem.slot];
         const bool fast = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]) &&
                           rec.pushPeer[0] < 0;
-        double accDens = 0.0;
-        double accWall[4] = {0.0, 0.0, 0.0, 0.0};
-        if (fast) item_compute<KPT, UPWIND, false>(P, sm, pr, cur, k, ownBase, nbrBase, total, colV, colI0, colI1, colOn, accDens, accWall);
-        else item_compute<KPT, UPWIND, true>(P, sm, pr, cur, k, ownBase, nbrBase, total, colV, colI0, colI1, colOn, accDens, accWall);
-
-        // ---- item epilogue: sum_v f' (Density) and absorbed flux (wall charge)
-        const bool anyWall = (rec.wallSlot[0] >= 0) | (rec.wallSlot[1] >= 0) | (rec.wallSlot[2] >= 0) | (rec.wallSlot[3] >= 0);
-        const int warp = tid >> 5, lane = tid & 31;
-        const double sd = warp_sum(accDens);
-        if (lane == 0) sm.red[warp * 5] = sd;
-        if (anyWall) {
-#pragma unroll
-            for (int f = 0; f < 4; f++) {
-                const double wv = warp_sum(accWall[f]);
-                if (lane == 0) sm.red[warp * 5 + 1 + f] = wv;
-            }
-        }
-        ownBase += cur.npl + 2;
-        nbrBase += cur.npl;
-        const Item done = cur;
-        w += G;
-        k++;
-        const bool more = haveNxt;
-        if (more) {
-            cur = nxt;
-            haveNxt = decode_item(p, w + G, total, nxt);
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const int nw = nthr >> 5;
-            double d = 0.0;
-            for (int q = 0; q < nw; q++) d += sm.red[q * 5];
-            p.densPartial[(size_t)done.tet * p.nChunks + done.chunk] = d;
-            if (anyWall) {
-                const TetRec& rd = sm.rec[(k - 1) & 1];
-                for (int f = 0; f < 4; f++) {
-                    if (rd.wallSlot[f] < 0) continue;
-                    double q2 = 0.0;
-                    for (int q = 0; q < nw; q++) q2 += sm.red[q * 5 + 1 + f];
-                    // charge * (timeStep * area * flux.Sum() * cellVolume), solver.cpp:173-177
-                    atomicAdd(p.wall + rd.wallSlot[f], p.wallScale * rd.area[f] * q2);
-                }
-            }
-        }
-        if (!more) break;
-        __syncthreads();                       // red[] and rec[(k-1)&1] are free again
-        if (haveNxt) load_rec((k + 1) & 1, nxt.tet);
-        __syncthreads();
-        if (tid == 0) produce(P, sm, pr, k, total);
+        if (fast) item_compute<KPT, UPWIND, false>(P, sm, cur, rec, cOwn, cNbr, colV, colI0, colI1, colOn);
+        else item_compute<KPT, UPWIND, true>(P, sm, cur, rec, cOwn, cNbr, colV, colI0, colI1, colOn);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sm.itemEmpty + cItem.slot);
+        cItem.advance(kItemRing);
     }
 }
 
 }  // namespace
 
-// Returns false when the velocity grid does not fit this layout (caller falls back).
+// Returns false when the velocity grid does not fit this layout (caller falls back).  On success
+// p.densSplit tells the caller how many partial sums per (tet, chunk) were written.
 bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, cudaEvent_t e0, cudaEvent_t e1)
 {
     const int n0 = sp.n[0], n1 = sp.n[1], n2 = sp.n[2];
+    (void)n2;
     if (n0 % 2) return false;
     const int PE = n0 * n1;
     if ((PE * 8) % 16) return false;
+    if (((size_t)sp.N * 8) % 16) return false;
     const int PV = PE / 2;
-    int nthr, kpt;
-    if (PV <= 512) {
-        nthr = ((PV + 31) / 32) * 32;
-        if (nthr < 128) nthr = 128;
-        kpt = 1;
-    } else if (PV <= 1024) {
-        nthr = ((PV / 2 + 31) / 32) * 32;
-        kpt = 2;
-    } else if (PV <= 1536) {
-        nthr = ((PV / 3 + 31) / 32) * 32;
-        kpt = 3;
-    } else {
-        return false;
-    }
-    if (nthr * kpt < PV) nthr += 32;
-    if (nthr > 512) return false;
+    const int kpt = (PV + kConsThreads - 1) / kConsThreads;
+    if (kpt > 4) return false;
     const size_t PB = (size_t)PE * 8;
-    const size_t fixed = (kOwnRing + 8) * 8 + 2 * sizeof(TetRec) + (size_t)2 * 4 * n2 * 8 + 16 * 5 * 8 + 256;
+    const size_t fixed = kItemRing * (sizeof(TetRec) + sizeof(ItemHdr)) + (4 * kMaxRing + 2 * kItemRing) * 8 + 128;
     const size_t maxSmem = 227 * 1024;
-    int S = 4;
-    while (S >= 2 && kOwnRing * PB + (size_t)S * 4 * PB + fixed > maxSmem) S--;
-    if (S < 2) return false;
-    const size_t smem = kOwnRing * PB + (size_t)S * 4 * PB + fixed;
+    // as many 4-plane neighbour sets as fit beside an own ring two planes deeper, both capped
+    int S = kMaxRing, OD = kMaxRing;
+    while (S > 2 && (size_t)std::min(kMaxRing, S + 2) * PB + (size_t)S * 4 * PB + fixed > maxSmem) S--;
+    OD = std::min(kMaxRing, S + 2);
+    if ((size_t)OD * PB + (size_t)S * 4 * PB + fixed > maxSmem) return false;
+    const size_t smem = (size_t)OD * PB + (size_t)S * 4 * PB + fixed;
 
-    TmaParams P;
+    if (!ctx->workCounter) VT_CUDA(cudaMalloc(&ctx->workCounter, sizeof(unsigned long long)));
+    BulkParams P;
     P.s = p;
+    P.OD = OD;
     P.S = S;
     P.planeElems = PE;
     P.PV = PV;
-    const long long total = (long long)ctx->nOwned * p.nChunks;
-    const int grid = (int)std::min<long long>(total, ctx->prop.multiProcessorCount);
+    P.queue = ctx->workCounter;
+    P.total = (long long)ctx->nOwned * p.nChunks;
+    const int grid = (int)std::min<long long>(P.total, ctx->prop.multiProcessorCount);
 
     auto launch = [&](auto kern) {
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VT_CUDA(cudaMemsetAsync(ctx->workCounter, 0, sizeof(unsigned long long), ctx->stream));
         VT_CUDA(cudaEventRecord(e0, ctx->stream));
-        kern<<<grid, nthr, smem, ctx->stream>>>(P);
+        kern<<<grid, kConsThreads + 32, smem, ctx->stream>>>(P);
         VT_CUDA(cudaEventRecord(e1, ctx->stream));
     };
-    if (kpt == 1) upwind ? launch(k_full_step_tma<1, true>) : launch(k_full_step_tma<1, false>);
-    else if (kpt == 2) upwind ? launch(k_full_step_tma<2, true>) : launch(k_full_step_tma<2, false>);
-    else upwind ? launch(k_full_step_tma<3, true>) : launch(k_full_step_tma<3, false>);
+    if (kpt == 1) upwind ? launch(k_full_step_bulk<1, true>) : launch(k_full_step_bulk<1, false>);
+    else if (kpt == 2) upwind ? launch(k_full_step_bulk<2, true>) : launch(k_full_step_bulk<2, false>);
+    else if (kpt == 3) upwind ? launch(k_full_step_bulk<3, true>) : launch(k_full_step_bulk<3, false>);
+    else upwind ? launch(k_full_step_bulk<4, true>) : launch(k_full_step_bulk<4, false>);
     VT_CUDA(cudaGetLastError());
+    p.densSplit = kConsWarps;
     return true;
 }
 

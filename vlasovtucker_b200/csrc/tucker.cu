@@ -41,6 +41,7 @@ struct TuckerState {
     int maxRank = 0;
     int cur = 0;
     bool vnabsValid = false;
+    bool denseValid = false;     // sp.f[sp.cur] holds the reconstruction of buf[cur]
 };
 
 namespace {
@@ -248,6 +249,7 @@ struct TuckerParams {
     const TetRec* rec;
     const double* E;
     const double* vnabs;   // [nOwned][4][N]
+    const double* src;     // dense source PDFs (Source BC), rows of N
     double* density;
     double* wall;
     double* scratch;       // per CTA: 5 N + 3 kMaxN*kMaxN(U work) doubles
@@ -351,8 +353,13 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
         double wallAcc[4] = {0, 0, 0, 0};
         for (int f = 0; f < 4; f++) {
             const int bc = rec.bc[f];
-            const bool pair = bc == VT_PBC_NONBOUNDARY || bc == VT_PBC_PERIODIC;
-            if (pair) {
+            const bool pair = bc == VT_PBC_NONBOUNDARY || bc == VT_PBC_PERIODIC || bc == VT_PBC_SOURCE;
+            if (bc == VT_PBC_SOURCE) {
+                // sourcePDF takes the neighbour's place (solver.cpp:335-338); kept dense on the device
+                const double* srow = P.src + (size_t)(-2 - rec.nbr[f]) * N;
+                for (int e = threadIdx.x; e < N; e += blockDim.x) B[e] = srow[e];
+                __syncthreads();
+            } else if (pair) {
                 const int nb = rec.nbr[f];
                 double *core, *U[3];
                 slot_ptrs(const_cast<double*>(P.in) + (size_t)nb * P.slot, P, core, U);
@@ -469,6 +476,7 @@ void fill_params(vt_ctx* ctx, Species& sp, TuckerState& ts, TuckerParams& P)
     P.rec = sp.rec;
     P.E = ctx->E;
     P.vnabs = ts.vnabs;
+    P.src = sp.src;
     P.density = sp.density;
     P.wall = sp.wall;
     P.scratch = ts.scratch;
@@ -516,6 +524,43 @@ int guard(F f)
     }
 }
 
+}  // namespace
+
+// Dense copy of the current Tucker tensors in sp.f[sp.cur] (the buffers the Full-format moment
+// and download kernels read), refreshed lazily after a step or an upload.
+void tucker_materialize(vt_ctx* ctx, Species& sp)
+{
+    TuckerState& ts = state_of(sp);
+    if (ts.denseValid) return;
+    TuckerParams P;
+    fill_params(ctx, sp, ts, P);
+    P.mode = 2;
+    P.in = ts.buf[ts.cur];
+    P.rin = ts.ranks[ts.cur];
+    P.denseOut = sp.f[sp.cur];
+    launch(ctx, ts, P);
+    ts.denseValid = true;
+}
+
+// Compress the dense rows in sp.f[sp.cur] into the Tucker state, exactly (precision 0) as
+// ParticleData<Tucker>::SetMaxwellPDF does (particle_data.cpp:64-69), ranks capped by the slot size.
+void tucker_from_dense(vt_ctx* ctx, Species& sp)
+{
+    TuckerState& ts = state_of(sp);
+    TuckerParams P;
+    fill_params(ctx, sp, ts, P);
+    P.mode = 1;
+    P.denseIn = sp.f[sp.cur];
+    P.out = ts.buf[ts.cur];
+    P.rout = ts.ranks[ts.cur];
+    launch(ctx, ts, P);
+    sp.densityValid = false;
+    // sp.f keeps the caller's tensors; they equal the reconstruction unless the rank cap binds
+    ts.denseValid = ts.maxRank >= std::max({sp.n[0], sp.n[1], sp.n[2]});
+}
+
+namespace {
+
 void ensure_vnabs(vt_ctx* ctx, Species& sp, TuckerState& ts)
 {
     if (ts.vnabsValid) return;
@@ -542,7 +587,13 @@ int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
         if (ctx->nGhost > 0) throw std::runtime_error("the Tucker path is single-GPU for now");
         for (int k = 0; k < 3; k++)
             if (sp.n[k] > kMaxN) throw std::runtime_error("Tucker path: velocity grid larger than 64 nodes per axis");
-        if (sp.tucker) tucker_destroy(sp.tucker);
+        if (sp.tucker) {
+            // re-configuration (SetCompressionError / SetMaxRank after the PDF was set): keep the state
+            tucker_materialize(ctx, sp);
+            VT_CUDA(cudaStreamSynchronize(ctx->stream));
+            tucker_destroy(sp.tucker);
+            sp.tucker = nullptr;
+        }
         TuckerState* ts = new TuckerState();
         sp.tucker = ts;
         ts->comprErr = comprErr;
@@ -562,31 +613,19 @@ int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
         ts->scratchCTAs = 2 * ctx->prop.multiProcessorCount;
         const size_t per = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
         VT_CUDA(cudaMalloc(&ts->scratch, (size_t)ts->scratchCTAs * per * sizeof(double)));
+        tucker_from_dense(ctx, sp);   // whatever the species holds (zeros after vt_species_create)
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
 
 int vt_tucker_set_pdf(vt_ctx* ctx, int species, const double* dense)
 {
-    return guard([&] {
-        VT_CUDA(cudaSetDevice(ctx->device));
-        Species& sp = species_of(ctx, species);
-        TuckerState& ts = state_of(sp);
-        const size_t bytes = (size_t)ctx->nOwned * sp.N * sizeof(double);
-        double* d = ctx_stage(ctx, bytes);
-        // caller order -> device order row by row
-        for (int p = 0; p < ctx->nOwned; p++)
-            VT_CUDA(cudaMemcpyAsync(d + (size_t)p * sp.N, dense + (size_t)ctx->order[p] * sp.N, (size_t)sp.N * sizeof(double),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-        TuckerParams P;
-        fill_params(ctx, sp, ts, P);
-        P.mode = 1;
-        P.denseIn = d;
-        P.out = ts.buf[ts.cur];
-        P.rout = ts.ranks[ts.cur];
-        launch(ctx, ts, P);
-        VT_CUDA(cudaStreamSynchronize(ctx->stream));
-        sp.densityValid = false;
-    });
+    // vt_species_set_pdf re-compresses a Tucker species after the upload
+    if (!ctx || species < 0 || species >= (int)ctx->species.size() || !ctx->species[species]->tucker) {
+        vt_set_error("species is not in Tucker format (vt_tucker_enable)");
+        return 1;
+    }
+    return vt_species_set_pdf(ctx, species, 0, ctx->nOwned, dense);
 }
 
 int vt_tucker_get_pdf(vt_ctx* ctx, int species, double* dense)
@@ -595,15 +634,9 @@ int vt_tucker_get_pdf(vt_ctx* ctx, int species, double* dense)
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
         TuckerState& ts = state_of(sp);
-        const size_t bytes = (size_t)ctx->nOwned * sp.N * sizeof(double);
-        double* d = ctx_stage(ctx, bytes);
-        TuckerParams P;
-        fill_params(ctx, sp, ts, P);
-        P.mode = 2;
-        P.in = ts.buf[ts.cur];
-        P.rin = ts.ranks[ts.cur];
-        P.denseOut = d;
-        launch(ctx, ts, P);
+        (void)ts;
+        tucker_materialize(ctx, sp);
+        const double* d = sp.f[sp.cur];
         for (int p = 0; p < ctx->nOwned; p++)
             VT_CUDA(cudaMemcpyAsync(dense + (size_t)ctx->order[p] * sp.N, d + (size_t)p * sp.N, (size_t)sp.N * sizeof(double),
                                     cudaMemcpyDeviceToHost, ctx->stream));
@@ -656,23 +689,9 @@ int vt_tucker_density(vt_ctx* ctx, int species, double* density)
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
         TuckerState& ts = state_of(sp);
-        if (!sp.densityValid) {
-            // Sum() of the current tensors: reconstruct and sum (particle_data.cpp:93-102)
-            std::vector<double> dense((size_t)ctx->nOwned * sp.N);
-            // device-side: reuse the reconstruct mode into the stage buffer, then the dense density kernel
-            double* d = ctx_stage(ctx, dense.size() * sizeof(double));
-            TuckerParams P;
-            fill_params(ctx, sp, ts, P);
-            P.mode = 2;
-            P.in = ts.buf[ts.cur];
-            P.rin = ts.ranks[ts.cur];
-            P.denseOut = d;
-            launch(ctx, ts, P);
-            double* keep = sp.f[sp.cur];
-            sp.f[sp.cur] = d;            // launch_density reads sp.f[sp.cur]
-            launch_density(ctx, sp);
-            sp.f[sp.cur] = keep;
-        }
+        (void)ts;
+        // Sum() of the current tensors (particle_data.cpp:93-102); launch_density materialises them
+        if (!sp.densityValid) launch_density(ctx, sp);
         if (density) {
             std::vector<double> tmp(ctx->nOwned);
             VT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -690,9 +709,6 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
         TuckerState& ts = state_of(sp);
         if (sp.danglingFaces > 0)
             throw std::runtime_error(std::to_string(sp.danglingFaces) + " boundary faces have no neighbour and no particle BC");
-        for (const auto& r : sp.recHost)
-            for (int f = 0; f < 4; f++)
-                if (r.bc[f] == VT_PBC_SOURCE) throw std::runtime_error("Source BC is not implemented on the Tucker path yet");
         ensure_vnabs(ctx, sp, ts);
         TuckerParams P;
         fill_params(ctx, sp, ts, P);
@@ -708,6 +724,7 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
         launch(ctx, ts, P);
         VT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
         ts.cur ^= 1;
+        ts.denseValid = false;
         sp.densityValid = true;
     });
 }

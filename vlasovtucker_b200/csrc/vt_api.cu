@@ -423,6 +423,7 @@ int vt_species_set_pdf(vt_ctx* ctx, int species, int first, int count, const dou
         vt::Species& sp = species_of(ctx, species);
         if (first < 0 || count < 0 || first + count > ctx->nOwned + ctx->nGhost)
             throw std::out_of_range("vt_species_set_pdf: tet range");
+        if (sp.tucker) vt::tucker_materialize(ctx, sp);   // partial ranges keep the other rows
         double* dst = sp.f[sp.cur];
         const size_t rowB = (size_t)sp.N * sizeof(double);
         // ghost rows and identity order: straight copies
@@ -442,6 +443,7 @@ int vt_species_set_pdf(vt_ctx* ctx, int species, int first, int count, const dou
         }
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
         sp.densityValid = false;
+        if (sp.tucker) vt::tucker_from_dense(ctx, sp);
     });
 }
 
@@ -452,6 +454,7 @@ int vt_species_get_pdf(vt_ctx* ctx, int species, int first, int count, double* p
         vt::Species& sp = species_of(ctx, species);
         if (first < 0 || count < 0 || first + count > ctx->nOwned + ctx->nGhost)
             throw std::out_of_range("vt_species_get_pdf: tet range");
+        if (sp.tucker) vt::tucker_materialize(ctx, sp);
         const double* src = sp.f[sp.cur];
         const size_t rowB = (size_t)sp.N * sizeof(double);
         if (ctx->identityOrder || first >= ctx->nOwned) {
@@ -524,6 +527,7 @@ int vt_species_set_maxwell(vt_ctx* ctx, int species, const double* physDensity, 
         }
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
         sp.densityValid = false;
+        if (sp.tucker) vt::tucker_from_dense(ctx, sp);
     });
 }
 
@@ -543,6 +547,7 @@ int vt_species_velocity(vt_ctx* ctx, int species, double* velocity)
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
         if (!sp.densityValid) vt::launch_density(ctx, sp);
+        if (sp.tucker) vt::tucker_materialize(ctx, sp);
         const int n = ctx->nOwned;
         double* vel = vt::ctx_stage(ctx, 3 * (size_t)std::max(1, n) * sizeof(double));
         if (n > 0) {

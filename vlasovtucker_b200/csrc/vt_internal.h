@@ -51,6 +51,7 @@ struct StepParams {
     int nvec0;            // n0 / VEC
     int nLG;              // line groups per CTA = blockDim / nvec0
     int chunkPlanes, nChunks, brickTets;
+    int densSplit;        // partial sums written per (tet, chunk): 1, or one per consumer warp
     double vmin[3], step[3], inv2h[3];
     double qm;            // charge / mass
     double ext[3];
@@ -144,6 +145,10 @@ extern "C" void vt_set_error(const char* msg);   // internal: sets vt_last_error
 namespace vt {
 void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3]);
 void launch_density(vt_ctx* ctx, Species& sp);
+// Tucker species: refresh the dense copy of the state in sp.f[sp.cur] (no-op when current)
+void tucker_materialize(vt_ctx* ctx, Species& sp);
+// Tucker species: re-compress the dense rows in sp.f[sp.cur] into the Tucker state (precision 0)
+void tucker_from_dense(vt_ctx* ctx, Species& sp);
 void poisson_destroy(PoissonData* p);
 double* ctx_stage(vt_ctx* ctx, size_t bytes);
 double* ctx_pinned(vt_ctx* ctx, size_t bytes);

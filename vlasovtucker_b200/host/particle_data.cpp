@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <iostream>
+#include <type_traits>
 
 #include "device.h"
 #include "full.h"
@@ -15,16 +16,10 @@ ParticleData<T>::ParticleData(const Mesh* mesh, const VelocityGrid* vGrid) : mas
 {
     _maxRank = *std::max_element(vGrid->nCells.begin(), vGrid->nCells.end());
     std::cout << "The maximum rank is " << _maxRank << "\n";
-}
-
-template <>
-ParticleData<Full>::ParticleData(const Mesh* mesh, const VelocityGrid* vGrid) : mass(1), charge(1), _mesh(mesh), _vGrid(vGrid)
-{
-    _maxRank = *std::max_element(vGrid->nCells.begin(), vGrid->nCells.end());
-    std::cout << "The maximum rank is " << _maxRank << "\n";
     _dev = device::ContextOf(mesh);
     const int32_t n[3] = {vGrid->nCells[0], vGrid->nCells[1], vGrid->nCells[2]};
     device::Check(vt_species_create(_dev->ctx, n, vGrid->minV.data(), vGrid->maxV.data(), mass, charge, &_species));
+    if (std::is_same<T, Tucker>::value) device::Check(vt_tucker_enable(_dev->ctx, _species, _comprErr, _maxRank));
 }
 
 template <typename T>
@@ -47,83 +42,73 @@ void ParticleData<Full>::SetMaxwellPDF(const MaxwellPDF& params)
 }
 
 template <>
+void ParticleData<Tucker>::SyncFromDevice()
+{
+    const int n0 = _vGrid->nCells[0], n1 = _vGrid->nCells[1], n2 = _vGrid->nCells[2];
+    std::vector<double> core((size_t)n0 * n1 * n2), u0((size_t)n0 * n0), u1((size_t)n1 * n1), u2((size_t)n2 * n2);
+    pdf.clear();
+    pdf.reserve(_mesh->tets.size());
+    for (size_t t = 0; t < _mesh->tets.size(); t++) {
+        int32_t r[3];
+        device::Check(vt_tucker_get_factors(_dev->ctx, _species, (int)t, r, core.data(), u0.data(), u1.data(), u2.data()));
+        Tensor3d c(r[0], r[1], r[2]);
+        std::copy(core.begin(), core.begin() + (size_t)r[0] * r[1] * r[2], c.data());
+        std::array<Eigen::MatrixXd, 3> u = {Eigen::MatrixXd(n0, r[0]), Eigen::MatrixXd(n1, r[1]), Eigen::MatrixXd(n2, r[2])};
+        std::copy(u0.begin(), u0.begin() + (size_t)n0 * r[0], u[0].data());
+        std::copy(u1.begin(), u1.begin() + (size_t)n1 * r[1], u[1].data());
+        std::copy(u2.begin(), u2.begin() + (size_t)n2 * r[2], u[2].data());
+        pdf.push_back(Tucker(c, u));
+    }
+}
+template <>
+void ParticleData<Full>::SyncFromDevice() {}
+
+template <>
 void ParticleData<Tucker>::SetMaxwellPDF(const MaxwellPDF& params)
 {
-    // host construction of the initial Tucker tensors (particle_data.cpp:23-90, uncompressed ranks)
-    const int n0 = _vGrid->nCells[0], n1 = _vGrid->nCells[1], n2 = _vGrid->nCells[2];
-    Tensor3d t3d(n0, n1, n2);
+    // the Maxwellian is tabulated and scaled on the device as for Full, then stored as exact Tucker
+    // tensors (precision 0, as particle_data.cpp:64-69 builds them)
+    PushParams();
+    device::Check(vt_species_set_maxwell(_dev->ctx, _species, params.physDensity.data(), params.temperature,
+                                         params.mostProbableV.data()));
+    SyncFromDevice();
     double reduction = 0;
-    pdf.clear();
-    for (auto* tet : _mesh->tets) {
-        if (params.temperature != 0.0) {
-            double normConst = 0;
-            for (int i0 = 0; i0 < n0; i0++)
-                for (int i1 = 0; i1 < n1; i1++)
-                    for (int i2 = 0; i2 < n2; i2++) {
-                        const Vector3d v = _vGrid->At(i0, i1, i2);
-                        double v2 = 0;
-                        for (int j = 0; j < 3; j++) v2 += (v[j] - params.mostProbableV[j]) * (v[j] - params.mostProbableV[j]);
-                        t3d(i0, i1, i2) = std::exp(-mass * v2 / (2 * boltzConst * params.temperature));
-                        normConst += t3d(i0, i1, i2);
-                    }
-            const double scale = params.physDensity[tet->index] / (_vGrid->cellVolume * normConst);
-            for (long i = 0; i < t3d.size(); i++) t3d.data()[i] *= scale;
-        } else {
-            t3d.setZero();
-            const int i0 = (int)((params.mostProbableV[0] - _vGrid->minV[0]) / _vGrid->step[0]);
-            const int i1 = (int)((params.mostProbableV[1] - _vGrid->minV[1]) / _vGrid->step[1]);
-            const int i2 = (int)((params.mostProbableV[2] - _vGrid->minV[2]) / _vGrid->step[2]);
-            t3d(i0, i1, i2) = params.physDensity[tet->index] / _vGrid->cellVolume;
-        }
-        Tucker tensor(t3d);
-        reduction += t3d.size() / (double)tensor.Size();
-        pdf.push_back(tensor);
-    }
+    for (const auto& t : pdf) reduction += _vGrid->nCellsTotal / (double)t.Size();
     std::cout << "PDF size reduction: " << reduction / (double)_mesh->tets.size() << " times on average\n";
 }
 
-template <>
-std::vector<double> ParticleData<Full>::Density() const
+// Density()/Velocity() (particle_data.cpp:93-128) are device reductions for both formats; a
+// Tucker species is reconstructed on the device first
+template <typename T>
+std::vector<double> ParticleData<T>::Density() const
 {
     std::vector<double> r(_mesh->tets.size());
     device::Check(vt_species_density(_dev->ctx, _species, r.data()));
     return r;
 }
-template <>
-std::vector<Vector3d> ParticleData<Full>::Velocity() const
+template <typename T>
+std::vector<Vector3d> ParticleData<T>::Velocity() const
 {
     std::vector<Vector3d> r(_mesh->tets.size());
     device::Check(vt_species_velocity(_dev->ctx, _species, &r[0][0]));
     return r;
 }
-template <>
-std::vector<double> ParticleData<Tucker>::Density() const
-{
-    std::vector<double> r(_mesh->tets.size());
-    for (size_t i = 0; i < r.size(); i++) r[i] = pdf[i].Sum() * _vGrid->cellVolume;
-    return r;
-}
-template <>
-std::vector<Vector3d> ParticleData<Tucker>::Velocity() const
-{
-    std::vector<Vector3d> r(_mesh->tets.size());
-    const std::vector<double> density = Density();
-    for (size_t i = 0; i < r.size(); i++)
-        for (int k = 0; k < 3; k++) {
-            const Tucker vPDF = Tucker(_vGrid->v[k]) * pdf[i];
-            r[i][k] = density[i] != 0 ? vPDF.Sum() * _vGrid->cellVolume / density[i] : 0.0;
-        }
-    return r;
-}
-
 template <typename T>
-void ParticleData<T>::SetCompressionError(double e) { _comprErr = e; }
+void ParticleData<T>::SetCompressionError(double e)
+{
+    _comprErr = e;
+    if (std::is_same<T, Tucker>::value) device::Check(vt_tucker_enable(_dev->ctx, _species, _comprErr, _maxRank));
+}
 template <typename T>
 double ParticleData<T>::CompressionError() const { return _comprErr; }
 template <typename T>
 int ParticleData<T>::MaxRank() const { return _maxRank; }
 template <typename T>
-void ParticleData<T>::SetMaxRank(int r) { _maxRank = r; }
+void ParticleData<T>::SetMaxRank(int r)
+{
+    _maxRank = r;
+    if (std::is_same<T, Tucker>::value) device::Check(vt_tucker_enable(_dev->ctx, _species, _comprErr, _maxRank));
+}
 
 template class ParticleData<Full>;
 template class ParticleData<Tucker>;

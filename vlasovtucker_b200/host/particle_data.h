@@ -1,6 +1,7 @@
 // Per-species state of the public API (reference: src/particle_data.h:21-59).  For
 // TensorType = Full the distribution function lives on the GPU and `pdf` holds row handles;
-// for TensorType = Tucker `pdf` holds host values (the device Tucker path is under construction).
+// for TensorType = Tucker the compressed tensors live on the GPU as well (vt_tucker_*) and `pdf`
+// is a host mirror (core + factors per tet) refreshed by SyncFromDevice().
 #pragma once
 #include <functional>
 #include <memory>
@@ -42,6 +43,7 @@ public:
     std::shared_ptr<device::MeshContext> DeviceContext() const { return _dev; }
     int DeviceSpecies() const { return _species; }
     void PushParams() const;        // mass/charge are public members assigned after construction
+    void SyncFromDevice();          // Tucker: refresh the host mirror `pdf` from the device state
 
 public:
     std::string species = "";

@@ -69,8 +69,8 @@ void Solver<T>::_InitializeWallCharge()
     }
 }
 
-template <>
-void Solver<Full>::_PushParticleBC()
+template <typename T>
+void Solver<T>::_PushParticleBC()
 {
     if (!_bcDirty) return;
     auto dev = _pData->DeviceContext();
@@ -96,8 +96,8 @@ void Solver<Full>::_PushParticleBC()
     _bcDirty = false;
 }
 
-template <>
-void Solver<Full>::_PullWallCharge()
+template <typename T>
+void Solver<T>::_PullWallCharge()
 {
     auto dev = _pData->DeviceContext();
     for (auto& kv : _wallCharge)
@@ -120,19 +120,24 @@ void Solver<Full>::_UpdatePDF()
 }
 
 template <>
-void Solver<Tucker>::_PushParticleBC() {}
-template <>
-void Solver<Tucker>::_PullWallCharge() {}
-template <>
 void Solver<Tucker>::_UpdatePDF()
 {
-    throw std::runtime_error(
-        "Solver<Tucker>::_UpdatePDF: the Tucker update has no device implementation yet and this library has no CPU "
-        "fallback");
+    _log << Indent(2) << "Compute the right-hand side\n";
+    _log << Indent(3) << "Boltzmann part\n";
+    _log << Indent(3) << "Vlasov part\n";
+    _log << Indent(2) << "Time integration\n";
+    _pData->PushParams();
+    _PushParticleBC();
+    auto dev = _pData->DeviceContext();
+    const double ext[3] = {externalField[0], externalField[1], externalField[2]};
+    // flux per face with rounding after each face, acceleration term, rounding, Euler update,
+    // rounding — all on the device (csrc/tucker.cu)
+    device::Check(vt_step_tucker(dev->ctx, _pData->DeviceSpecies(), timeStep, ext));
+    if (!_wallCharge.empty()) _PullWallCharge();
 }
 
-template <>
-void Solver<Full>::Solve()
+template <typename T>
+void Solver<T>::Solve()
 {
     _pData->PushParams();
     _PushParticleBC();   // also restarts the device wall-charge accumulators
@@ -175,15 +180,11 @@ void Solver<Full>::Solve()
             device::Check(vt_field_get(dev->ctx, _rho.data(), nullptr, nullptr));
             _phi = _poissonSolver.Potential();
             _field = _poissonSolver.ElectricField();
+            _pData->SyncFromDevice();   // Tucker: the host mirror feeds the distribution dump
             _WriteResults(iteration);
         }
     }
-}
-
-template <>
-void Solver<Tucker>::Solve()
-{
-    _UpdatePDF();
+    _pData->SyncFromDevice();
 }
 
 template <typename T>
