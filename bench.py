@@ -108,11 +108,14 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+def ncu_traffic(kernel):
+    """dram bytes per launch of the step kernel from the committed ncu capture of the default
+    bench command (profiles/k_full_step_traffic.json, written from an `ncu --set full` report by
+    scripts/ncu_summary.py), if it is for the kernel this run uses."""
     p = os.path.join(ROOT, "profiles", "k_full_step_traffic.json")
     try:
-        return json.load(open(p))
+        d = json.load(open(p))
+        return d if d.get("kernel") == kernel else None
     except Exception:
         return None
 
@@ -277,7 +280,9 @@ def run_gpu(args):
         peak, peak_src = measured_peak()
         kern_avg_ms = kern_ms / max(1, kern_n)
         achieved = ALGO_BYTES_PER_UPDATE * updates_rank / (kern_avg_ms * 1e-3) / 1e9
-        tr = ncu_traffic()
+        bulk = (args.variant & 64 and nv % 2 == 0 and nv * nv * 8 >= 4096) or (args.variant & 16)
+        kernel_name = "k_full_step_bulk" if bulk else "k_full_step"
+        tr = ncu_traffic(kernel_name)
         line = {
             "metric": "cell x v-node updates/s per step (full format)", "value": value, "unit": "updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -288,11 +293,12 @@ def run_gpu(args):
                 "tets_per_gpu": nT, "v_nodes": N, "state_bytes_per_gpu": 2 * nT * N * 8,
                 "l2_policy": "inputs larger than L2 (state is %.1f GB per copy); no flush needed" % (nT * N * 8 / 1e9),
                 "brick_hexes": list(args.brick), "chunk_planes": args.chunk_planes, "kernel_variant": args.variant,
+                "kernel": kernel_name,
                 "step": "K1 full_step (flux+accel+Euler+density partials) + density reduce" + ("; halo push over NVLink" if world > 1 else ""),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None if tr is None else tr.get("dram_bytes_per_launch"),
-                         "peak_source": peak_src, "kernel": "k_full_step", "kernel_ms": kern_avg_ms,
+                         "peak_source": peak_src, "kernel": kernel_name, "kernel_ms": kern_avg_ms,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_UPDATE * updates_rank,
                          "kernel_share_of_step": kern_ms / region_ms},
             "e2e": {"value": e2e_value, "unit": "updates/s", "h2d_bytes_per_step": 3 * nT * 8 * world,
@@ -320,7 +326,9 @@ def main():
     ap.add_argument("--nv", type=int, default=32)
     ap.add_argument("--brick", type=int, nargs=3, default=[4, 4, 4], help="L2 brick in hexes")
     ap.add_argument("--chunk-planes", type=int, default=0, help="i2-planes per work item (0 = whole tensor)")
-    ap.add_argument("--variant", type=int, default=2, help="vt_step_config variant bits (2 = upwind-select arithmetic)")
+    ap.add_argument("--variant", type=int, default=64,
+                    help="vt_step_config variant bits; 64 = the library's own choice (bulk-copy pipeline, upwind-select "
+                         "arithmetic for 32^3), 2 = register-staged kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -104,8 +104,15 @@ int vt_step_full(vt_ctx* ctx, int species, double dt, const double ext[3]);
  * E (3*nOwned doubles) host->device, steps, copies Density() (nOwned doubles) device->host */
 int vt_step_full_host(vt_ctx* ctx, int species, double dt, const double ext[3], const double* E,
                       double* density);
-/* tuning knobs of the step kernel: planes of the velocity grid per CTA (0 = whole tensor) and
- * tets per L2 brick (0 = default) */
+/* tuning knobs of the step kernel: planes of the velocity grid per work item (0 = whole tensor),
+ * tets per L2 brick (0 = no bricks) and the kernel variant as a bit set:
+ *   64 the library's choice from the velocity grid (the default: bulk-copy pipeline where planes of
+ *      >= 4 KiB can be staged, register-staged kernel otherwise, upwind-select arithmetic);
+ *    1 no warp shuffles, 2 upwind-select arithmetic (vn>0 ? vn*f : vn*fa instead of the reference's
+ *      0.5*(vn*(fa+f) - |vn|*(fa-f)); equal up to rounding), 4 three resident CTAs per SM,
+ *    8 persistent cp.async pipeline, 16 persistent bulk-copy (cp.async.bulk + mbarrier)
+ *      producer/consumer pipeline, 32 with 16: eight consumer warps x two columns instead of sixteen.
+ * Every variant computes the same update; they differ in scheduling only (tests/test_full_gpu.py). */
 int vt_step_config(vt_ctx* ctx, int chunkPlanes, int brickTets, int variant);
 /* device time of the last vt_step_full kernel in milliseconds (CUDA events) and launches so far */
 int vt_step_last_ms(vt_ctx* ctx, float* ms);

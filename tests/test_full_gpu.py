@@ -88,6 +88,12 @@ def _run_pair(vt, oracle_mod, m, n, vmin, vmax, mass, charge, f0, E, dt, steps, 
     ((48, 48, 3), None, 0, 18),           # TMA, 3 columns per thread
     ((50, 5, 5), None, None, None),       # sheath grid
     ((50, 5, 5), None, None, 10),
+    ((32, 32, 4), None, 0, None),         # library default at the bench plane size: bulk-copy pipeline, 8 warps x 2 columns
+    ((32, 32, 4), 2, 0, 18),              # bulk-copy pipeline, 16 consumer warps, 2-plane items
+    ((32, 32, 5), 1, 64, 50),             # single-plane items through the queue, bricks of 64 tets
+    ((32, 32, 4), 2, 0, 0),               # register-staged kernel, reference expression shape
+    ((64, 64, 3), None, 0, 18),           # 4 columns per consumer thread, 32 KiB planes (ring depth 1x... 4)
+    ((24, 22, 4), 3, 0, 16),              # plane not a multiple of the consumer count, reference arithmetic
 ])
 def test_update_pdf_periodic_parity(vt, oracle_mod, n, chunk, brick, variant):
     m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(1, 2), (3, 4), (5, 6)])
@@ -154,16 +160,17 @@ def test_maxwellian_init_bit_exact(vt, oracle_mod):
     ctx.close()
 
 
-def test_wall_bcs_and_charge(vt, oracle_mod):
+@pytest.mark.parametrize("n,variant", [((50, 5, 5), None), ((32, 16, 5), 18), ((32, 32, 4), 50)])
+def test_wall_bcs_and_charge(vt, oracle_mod, n, variant):
     """Sheath-style boundaries (examples/sheath.cpp:100-110): entity 1 Absorbing+collectCharge,
     entity 2 Free, {3,4},{5,6} periodic; wall charge as solver.cpp:171-178."""
     m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(3, 4), (5, 6)])
-    n, vmin, vmax = (50, 5, 5), [-4, -1, -1], [4, 1, 1]
+    vmin, vmax = [-4, -1, -1], [4, 1, 1]
     f0 = _smooth_state(m, n, vmin, vmax, seed=3)
     rng = np.random.default_rng(7)
     E = rng.standard_normal((m.nTets, 3))
     spec = {1: ("Absorbing", True), 2: ("Free", False)}
-    s, sp, ctx, g = _run_pair(vt, oracle_mod, m, n, vmin, vmax, 2.0, -3.0, f0, E, 2e-4, 4, bc_spec=spec)
+    s, sp, ctx, g = _run_pair(vt, oracle_mod, m, n, vmin, vmax, 2.0, -3.0, f0, E, 2e-4, 4, bc_spec=spec, variant=variant)
     s.init_wall()
     for _ in range(4):
         s.update_pdf(sp, E)
@@ -176,15 +183,16 @@ def test_wall_bcs_and_charge(vt, oracle_mod):
     ctx.close()
 
 
-def test_source_bc(vt, oracle_mod):
+@pytest.mark.parametrize("n,variant", [((8, 6, 4), None), ((32, 16, 4), 18)])
+def test_source_bc(vt, oracle_mod, n, variant):
     """Source faces use ParticleBC::sourcePDF in place of the neighbour (solver.cpp:334-339)."""
     m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(3, 4), (5, 6)])
-    n, vmin, vmax = (8, 6, 4), [-4, -1, -1], [4, 1, 1]
+    vmin, vmax = [-4, -1, -1], [4, 1, 1]
     f0 = _smooth_state(m, n, vmin, vmax, seed=4)
     src = 2.0 * f0[17].copy()
     E = np.zeros((m.nTets, 3))
     spec = {1: ("Source", False), 2: ("Absorbing", False)}
-    s, sp, ctx, g = _run_pair(vt, oracle_mod, m, n, vmin, vmax, 1.0, 1.0, f0, E, 1e-4, 3, bc_spec=spec, source=src)
+    s, sp, ctx, g = _run_pair(vt, oracle_mod, m, n, vmin, vmax, 1.0, 1.0, f0, E, 1e-4, 3, bc_spec=spec, source=src, variant=variant)
     for _ in range(3):
         s.update_pdf(sp, E)
         ctx.step_full(g, 1e-4)

@@ -151,7 +151,7 @@ class Context:
         capi.check(self.lib.vt_step_full_host(self.h, sp, float(dt), capi.dp(ext), capi.dp(E), capi.dp(density_out)))
 
     def step_config(self, chunk_planes=None, brick_tets=None, variant=None):
-        self._cfg = getattr(self, "_cfg", [0, 0, 0])
+        self._cfg = getattr(self, "_cfg", [0, 0, 64])
         if chunk_planes is not None:
             self._cfg[0] = int(chunk_planes)
         if brick_tets is not None:

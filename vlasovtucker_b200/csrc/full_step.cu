@@ -349,6 +349,19 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
         throw std::runtime_error(std::to_string(sp.danglingFaces) +
                                  " boundary faces have no neighbour and no particle BC (Absorbing/Free/Source); "
                                  "the reference dereferences a null adjTets there (solver.cpp:319)");
+    // variant bit 6 (the default): pick the kernel from the grid — the bulk-copy pipeline with eight
+    // consumer warps and the upwind-select arithmetic where whole planes of >= 4 KiB can be staged,
+    // the register-staged kernel otherwise.  Explicit bits are honoured as given.
+    struct VariantScope {
+        vt_ctx* c;
+        int saved;
+        ~VariantScope() { c->variant = saved; }
+    } variantScope{ctx, ctx->variant};
+    if (ctx->variant & 64) {
+        const int PE = sp.n[0] * sp.n[1];
+        const bool planes = sp.n[0] % 2 == 0 && PE * 8 >= 4096 && PE / 2 <= 2048;
+        ctx->variant = planes ? (2 | 16 | 32) : 2;
+    }
     StepParams p;
     p.f = sp.f[sp.cur];
     p.fn = sp.f[sp.cur ^ 1];
@@ -386,7 +399,7 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
     for (int i = 0; i < kMaxPeers; i++) p.peerFn[i] = i < sp.nPeers ? sp.peerF[i][sp.cur ^ 1] : nullptr;
 
     p.densSplit = 1;
-    const size_t need = (size_t)ctx->nOwned * p.nChunks * ((ctx->variant & 16) ? 8 : 1);
+    const size_t need = (size_t)ctx->nOwned * p.nChunks * ((ctx->variant & 16) ? 16 : 1);
     if (need > 2147483647ULL) throw std::runtime_error("vt_step_full: too many density partial sums");
     if ((size_t)sp.densPartialCap < need) {
         if (sp.densPartial) VT_CUDA(cudaFree(sp.densPartial));

@@ -31,8 +31,6 @@ namespace vt {
 
 namespace {
 
-constexpr int kConsWarps = 8;
-constexpr int kConsThreads = kConsWarps * 32;
 constexpr int kItemRing = 4;
 constexpr int kMaxRing = 16;
 
@@ -222,13 +220,60 @@ __device__ void producer_loop(const BulkParams& P, const Smem& sm)
 
 // ---- consumers: all planes of one work item.  GENERIC: per-face boundary conditions and halo
 // push (branches are uniform across the CTA); otherwise four pair faces and no push.
-template <int KPT, bool UPWIND, bool GENERIC>
-__device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm, const ItemHdr& cur, const TetRec& rec,
-                                             Cursor& cOwn, Cursor& cNbr, const int (&colV)[KPT], const int (&colI0)[KPT],
-                                             const int (&colI1)[KPT], const bool (&colOn)[KPT])
+// Per-thread constants of one column (fixed for the whole kernel): byte offset of its double2 inside
+// a plane and of its i1-1 / i1+1 / i0-1 / i0+2 neighbours (periodic wrap), all relative to the
+// plane start.
+struct Column {
+    uint32_t evB, dUmB, dUpB, dFlB, dFrB;
+    int i0, i1;
+    bool on;
+};
+
+__device__ __forceinline__ double2 lds128(uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait32(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive32(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Consumer-side view of the rings: 32-bit shared addresses, ring depths are powers of two so a
+// stage counter gives slot = c & mask and parity = (c >> shift) & 1.
+struct ConsRings {
+    uint32_t own, nbr;                       // ring data
+    uint32_t ownFull, ownEmpty, nbrFull, nbrEmpty;
+    uint32_t PB;                             // bytes per plane
+    uint32_t odMask, odShift, sMask, sShift;
+};
+
+template <int KPT, bool UPWIND, bool GENERIC, int NCW>
+__device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRings& R, const ItemHdr& cur, const TetRec& rec,
+                                             uint32_t& cOwn, uint32_t& cNbr, const Column (&col)[KPT])
 {
     const StepParams& p = P.s;
-    const int PE = P.planeElems;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     double cxy[KPT][4][2], hc[4], cz[4];
@@ -241,13 +286,13 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
         colF[f] = GENERIC && rec.wallSlot[f] >= 0;
         hc[f] = pairF[f] ? 0.5 * rec.coef[f] : rec.coef[f];
         const double pre = (UPWIND && pairF[f]) ? rec.coef[f] : 1.0;
-        cz[f] = pre;
+        cz[f] = pre * rec.nrm[f][2];
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
-            const double v1 = __dadd_rn(p.vmin[1], __dmul_rn((double)colI1[kk], p.step[1]));
+            const double v1 = __dadd_rn(p.vmin[1], __dmul_rn((double)col[kk].i1, p.step[1]));
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-                const double v0 = __dadd_rn(p.vmin[0], __dmul_rn((double)(colI0[kk] + u), p.step[0]));
+                const double v0 = __dadd_rn(p.vmin[0], __dmul_rn((double)(col[kk].i0 + u), p.step[0]));
                 cxy[kk][f][u] = pre * (rec.nrm[f][0] * v0 + rec.nrm[f][1] * v1);
             }
         }
@@ -255,64 +300,75 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
     double g[3];
 #pragma unroll
     for (int q = 0; q < 3; q++) g[q] = (p.qm * (cur.E[q] + p.ext[q])) * p.inv2h[q];
-    double* nrow = p.fn + (size_t)cur.tet * p.N;
-    double* push[4] = {nullptr, nullptr, nullptr, nullptr};
+    // running output pointers (advance one plane per iteration)
+    char* outp[KPT];
+#pragma unroll
+    for (int kk = 0; kk < KPT; kk++)
+        outp[kk] = reinterpret_cast<char*>(p.fn + (size_t)cur.tet * p.N + (size_t)cur.pl0 * P.planeElems) + col[kk].evB;
+    long long pushOff[4] = {0, 0, 0, 0};   // byte distance from this tet's row to its ghost copies
+    bool pushOn[4] = {false, false, false, false};
     if (GENERIC) {
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            if (rec.pushPeer[q] >= 0) push[q] = p.peerFn[rec.pushPeer[q]] + (size_t)rec.pushRow[q] * p.N;
+            if (rec.pushPeer[q] >= 0) {
+                pushOn[q] = true;
+                pushOff[q] = reinterpret_cast<char*>(p.peerFn[rec.pushPeer[q]] + (size_t)rec.pushRow[q] * p.N) -
+                             reinterpret_cast<char*>(p.fn + (size_t)cur.tet * p.N);
+            }
     }
     double accDens = 0.0;
     double accWall[4] = {0.0, 0.0, 0.0, 0.0};
 
     // own stages 0 and 1: prev (registers only) and cur (registers + i0/i1 neighbours from smem)
     double2 prv[KPT], cr[KPT];
-    mbar_wait(sm.ownFull + cOwn.slot, cOwn.phase);
     {
-        const double* s0 = sm.ownRing + (size_t)cOwn.slot * PE;
+        const uint32_t slot = cOwn & R.odMask;
+        mbar_wait32(R.ownFull + slot * 8, (cOwn >> R.odShift) & 1u);
+        const uint32_t a = R.own + slot * R.PB;
 #pragma unroll
-        for (int kk = 0; kk < KPT; kk++) prv[kk] = *reinterpret_cast<const double2*>(s0 + 2 * colV[kk]);
+        for (int kk = 0; kk < KPT; kk++) prv[kk] = lds128(a + col[kk].evB);
+        __syncwarp();
+        if (lane == 0) mbar_arrive32(R.ownEmpty + slot * 8);
+        cOwn++;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(sm.ownEmpty + cOwn.slot);
-    cOwn.advance(P.OD);
-    mbar_wait(sm.ownFull + cOwn.slot, cOwn.phase);
-    const double* sc = sm.ownRing + (size_t)cOwn.slot * PE;
-    int scSlot = cOwn.slot;
-    cOwn.advance(P.OD);
+    uint32_t scSlot = cOwn & R.odMask;
+    mbar_wait32(R.ownFull + scSlot * 8, (cOwn >> R.odShift) & 1u);
+    uint32_t scA = R.own + scSlot * R.PB;
+    cOwn++;
 #pragma unroll
-    for (int kk = 0; kk < KPT; kk++) cr[kk] = *reinterpret_cast<const double2*>(sc + 2 * colV[kk]);
+    for (int kk = 0; kk < KPT; kk++) cr[kk] = lds128(scA + col[kk].evB);
 
+    double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)cur.pl0, p.step[2]));
     for (int j = 0; j < cur.npl; j++) {
-        mbar_wait(sm.ownFull + cOwn.slot, cOwn.phase);
-        const double* sn = sm.ownRing + (size_t)cOwn.slot * PE;       // plane j+1
-        const int snSlot = cOwn.slot;
-        cOwn.advance(P.OD);
-        mbar_wait(sm.nbrFull + cNbr.slot, cNbr.phase);
-        const double* sb = sm.nbrRing + (size_t)cNbr.slot * 4 * PE;
-        const int nbSlot = cNbr.slot;
-        cNbr.advance(P.S);
+        const uint32_t snSlot = cOwn & R.odMask;
+        mbar_wait32(R.ownFull + snSlot * 8, (cOwn >> R.odShift) & 1u);
+        const uint32_t snA = R.own + snSlot * R.PB;       // plane j+1
+        cOwn++;
+        const uint32_t nbSlot = cNbr & R.sMask;
+        mbar_wait32(R.nbrFull + nbSlot * 8, (cNbr >> R.sShift) & 1u);
+        const uint32_t sbA = R.nbr + nbSlot * 4 * R.PB;
+        cNbr++;
 
-        const double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + j), p.step[2]));
         double tzf[4];
 #pragma unroll
-        for (int f = 0; f < 4; f++) tzf[f] = cz[f] * (rec.nrm[f][2] * v2);
-        const size_t gplane = (size_t)(cur.pl0 + j) * PE;
+        for (int f = 0; f < 4; f++) tzf[f] = cz[f] * v2;
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
-            if (!colOn[kk]) continue;
-            const int ev = 2 * colV[kk];
-            const int i0 = colI0[kk], i1 = colI1[kk];
-            const double2 nx = *reinterpret_cast<const double2*>(sn + ev);
-            const double2 um = *reinterpret_cast<const double2*>(sc + ev + ((i1 == 0) ? (p.n1 - 1) : -1) * p.n0);
-            const double2 up = *reinterpret_cast<const double2*>(sc + ev + ((i1 == p.n1 - 1) ? -(p.n1 - 1) : 1) * p.n0);
-            const double fl = sc[ev + ((i0 == 0) ? (p.n0 - 1) : -1)];
-            const double fr = sc[ev + 1 + ((i0 + 2 == p.n0) ? -(p.n0 - 1) : 1)];
+            if (!col[kk].on) continue;
+            const double2 nx = lds128(snA + col[kk].evB);
+            const double2 um = lds128(scA + col[kk].dUmB);
+            const double2 up = lds128(scA + col[kk].dUpB);
+            const double fl = lds64(scA + col[kk].dFlB);
+            const double fr = lds64(scA + col[kk].dFrB);
             double2 fa[4];
+            {
+                uint32_t a = sbA + col[kk].evB;
 #pragma unroll
-            for (int f = 0; f < 4; f++)
-                fa[f] = (!GENERIC || pairF[f]) ? *reinterpret_cast<const double2*>(sb + (size_t)f * PE + ev)
-                                               : make_double2(0.0, 0.0);
+                for (int f = 0; f < 4; f++) {
+                    fa[f] = (!GENERIC || pairF[f]) ? lds128(a) : make_double2(0.0, 0.0);
+                    a += R.PB;
+                }
+            }
             const double fcv[2] = {cr[kk].x, cr[kk].y};
             const double xm[2] = {fl, cr[kk].x};
             const double xp[2] = {cr[kk].y, fr};
@@ -349,30 +405,32 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
                 accDens += out[u];
             }
             const double2 o = make_double2(out[0], out[1]);
-            *reinterpret_cast<double2*>(nrow + gplane + ev) = o;
+            *reinterpret_cast<double2*>(outp[kk]) = o;
             if (GENERIC) {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    if (push[q]) *reinterpret_cast<double2*>(push[q] + gplane + ev) = o;
+                    if (pushOn[q]) *reinterpret_cast<double2*>(outp[kk] + pushOff[q]) = o;
             }
+            outp[kk] += R.PB;
             prv[kk] = cr[kk];
             cr[kk] = nx;
         }
+        v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + j + 1), p.step[2]));
         __syncwarp();   // every lane is done with own stage sc and neighbour slot nbSlot
         if (lane == 0) {
-            mbar_arrive(sm.ownEmpty + scSlot);
-            mbar_arrive(sm.nbrEmpty + nbSlot);
+            mbar_arrive32(R.ownEmpty + scSlot * 8);
+            mbar_arrive32(R.nbrEmpty + nbSlot * 8);
         }
-        sc = sn;
+        scA = snA;
         scSlot = snSlot;
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(sm.ownEmpty + scSlot);   // the last own stage (plane pl0+npl)
+    if (lane == 0) mbar_arrive32(R.ownEmpty + scSlot * 8);   // the last own stage (plane pl0+npl)
 
     // ---- item epilogue: sum_v f' (Density) per warp, reduced in fixed order by k_density_reduce;
     // absorbed flux (wall charge)
     const double sd = warp_sum(accDens);
-    if (lane == 0) p.densPartial[((size_t)cur.tet * p.nChunks + cur.chunk) * kConsWarps + warp] = sd;
+    if (lane == 0) p.densPartial[((size_t)cur.tet * p.nChunks + cur.chunk) * NCW + warp] = sd;
     if (GENERIC) {
 #pragma unroll
         for (int f = 0; f < 4; f++) {
@@ -384,8 +442,8 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
     }
 }
 
-template <int KPT, bool UPWIND>
-__global__ void __launch_bounds__(kConsThreads + 32, 1) k_full_step_bulk(const BulkParams P)
+template <int KPT, bool UPWIND, int NCW, bool ALLFAST>
+__global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkParams P)
 {
     const StepParams& p = P.s;
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -406,51 +464,87 @@ __global__ void __launch_bounds__(kConsThreads + 32, 1) k_full_step_bulk(const B
     if (tid == 0) {
         for (int i = 0; i < P.OD; i++) {
             mbar_init(sm.ownFull + i, 1);
-            mbar_init(sm.ownEmpty + i, kConsWarps);
+            mbar_init(sm.ownEmpty + i, NCW);
         }
         for (int i = 0; i < P.S; i++) {
             mbar_init(sm.nbrFull + i, 1);
-            mbar_init(sm.nbrEmpty + i, kConsWarps);
+            mbar_init(sm.nbrEmpty + i, NCW);
         }
         for (int i = 0; i < kItemRing; i++) {
             mbar_init(sm.itemFull + i, 2);
-            mbar_init(sm.itemEmpty + i, kConsWarps);
+            mbar_init(sm.itemEmpty + i, NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (tid >= kConsThreads) {
-        if (tid == kConsThreads) producer_loop(P, sm);
+    if (tid >= NCW * 32) {
+        if (tid == NCW * 32) producer_loop(P, sm);
         return;
     }
 
     // fixed columns of this consumer thread
-    int colV[KPT], colI0[KPT], colI1[KPT];
-    bool colOn[KPT];
+    Column col[KPT];
 #pragma unroll
     for (int kk = 0; kk < KPT; kk++) {
-        const int v = tid + kk * kConsThreads;
-        colOn[kk] = v < P.PV;
-        colV[kk] = colOn[kk] ? v : 0;
-        colI0[kk] = (colV[kk] % p.nvec0) * 2;
-        colI1[kk] = colV[kk] / p.nvec0;
+        const int v = tid + kk * NCW * 32;
+        col[kk].on = v < P.PV;
+        const int cv = col[kk].on ? v : 0;
+        const int i0 = (cv % p.nvec0) * 2, i1 = cv / p.nvec0;
+        col[kk].i0 = i0;
+        col[kk].i1 = i1;
+        col[kk].evB = 16u * cv;
+        col[kk].dUmB = 8u * (uint32_t)(2 * cv + ((i1 == 0) ? (p.n1 - 1) : -1) * p.n0);
+        col[kk].dUpB = 8u * (uint32_t)(2 * cv + ((i1 == p.n1 - 1) ? -(p.n1 - 1) : 1) * p.n0);
+        col[kk].dFlB = 8u * (uint32_t)(2 * cv + ((i0 == 0) ? (p.n0 - 1) : -1));
+        col[kk].dFrB = 8u * (uint32_t)(2 * cv + 1 + ((i0 + 2 == p.n0) ? -(p.n0 - 1) : 1));
     }
-    Cursor cItem, cOwn, cNbr;
+    ConsRings R;
+    R.own = smem_u32(sm.ownRing);
+    R.nbr = smem_u32(sm.nbrRing);
+    R.ownFull = smem_u32(sm.ownFull);
+    R.ownEmpty = smem_u32(sm.ownEmpty);
+    R.nbrFull = smem_u32(sm.nbrFull);
+    R.nbrEmpty = smem_u32(sm.nbrEmpty);
+    R.PB = (uint32_t)PE * 8u;
+    R.odMask = (uint32_t)P.OD - 1u;
+    R.odShift = 31u - (uint32_t)__clz(P.OD);
+    R.sMask = (uint32_t)P.S - 1u;
+    R.sShift = 31u - (uint32_t)__clz(P.S);
+    Cursor cItem;
+    uint32_t cOwn = 0, cNbr = 0;
     const int lane = tid & 31;
     while (true) {
         mbar_wait(sm.itemFull + cItem.slot, cItem.phase);
         const ItemHdr cur = sm.hdr[cItem.slot];
         if (cur.tet < 0) break;
         const TetRec& rec = sm.rec[cItem.slot];
-        const bool fast = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]) &&
-                          rec.pushPeer[0] < 0;
-        if (fast) item_compute<KPT, UPWIND, false>(P, sm, cur, rec, cOwn, cNbr, colV, colI0, colI1, colOn);
-        else item_compute<KPT, UPWIND, true>(P, sm, cur, rec, cOwn, cNbr, colV, colI0, colI1, colOn);
+        if (ALLFAST) {
+            item_compute<KPT, UPWIND, false, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+        } else {
+            const bool fast = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]) &&
+                              rec.pushPeer[0] < 0;
+            if (fast) item_compute<KPT, UPWIND, false, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+            else item_compute<KPT, UPWIND, true, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.itemEmpty + cItem.slot);
         cItem.advance(kItemRing);
     }
+}
+
+template <int KPT, int NCW>
+void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, int grid, size_t smem, cudaEvent_t e0, cudaEvent_t e1)
+{
+    auto launch = [&](auto kern) {
+        VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VT_CUDA(cudaMemsetAsync(ctx->workCounter, 0, sizeof(unsigned long long), ctx->stream));
+        VT_CUDA(cudaEventRecord(e0, ctx->stream));
+        kern<<<grid, NCW * 32 + 32, smem, ctx->stream>>>(P);
+        VT_CUDA(cudaEventRecord(e1, ctx->stream));
+    };
+    if (allFast) upwind ? launch(k_full_step_bulk<KPT, true, NCW, true>) : launch(k_full_step_bulk<KPT, false, NCW, true>);
+    else upwind ? launch(k_full_step_bulk<KPT, true, NCW, false>) : launch(k_full_step_bulk<KPT, false, NCW, false>);
 }
 
 }  // namespace
@@ -459,25 +553,38 @@ __global__ void __launch_bounds__(kConsThreads + 32, 1) k_full_step_bulk(const B
 // p.densSplit tells the caller how many partial sums per (tet, chunk) were written.
 bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, cudaEvent_t e0, cudaEvent_t e1)
 {
-    const int n0 = sp.n[0], n1 = sp.n[1], n2 = sp.n[2];
-    (void)n2;
+    const int n0 = sp.n[0], n1 = sp.n[1];
     if (n0 % 2) return false;
     const int PE = n0 * n1;
     if ((PE * 8) % 16) return false;
     if (((size_t)sp.N * 8) % 16) return false;
     const int PV = PE / 2;
-    const int kpt = (PV + kConsThreads - 1) / kConsThreads;
+    // variant bit 5: eight consumer warps with two columns per thread instead of sixteen with one
+    const bool wide = (ctx->variant & 32) != 0 && PV > 256 && PV <= 512;
+    const int ncw = wide ? 8 : 16;
+    const int kpt = (PV + ncw * 32 - 1) / (ncw * 32);
     if (kpt > 4) return false;
     const size_t PB = (size_t)PE * 8;
     const size_t fixed = kItemRing * (sizeof(TetRec) + sizeof(ItemHdr)) + (4 * kMaxRing + 2 * kItemRing) * 8 + 128;
     const size_t maxSmem = 227 * 1024;
-    // as many 4-plane neighbour sets as fit beside an own ring two planes deeper, both capped
+    // ring depths are powers of two (the consumers derive slot and parity from a stage counter)
     int S = kMaxRing, OD = kMaxRing;
-    while (S > 2 && (size_t)std::min(kMaxRing, S + 2) * PB + (size_t)S * 4 * PB + fixed > maxSmem) S--;
-    OD = std::min(kMaxRing, S + 2);
+    while (S > 2 && (size_t)S * 4 * PB + (size_t)4 * PB + fixed > maxSmem) S /= 2;
+    while (OD > 4 && (size_t)OD * PB + (size_t)S * 4 * PB + fixed > maxSmem) OD /= 2;
     if ((size_t)OD * PB + (size_t)S * 4 * PB + fixed > maxSmem) return false;
     const size_t smem = (size_t)OD * PB + (size_t)S * 4 * PB + fixed;
 
+    if (sp.fastOnly < 0) {
+        // every face paired with a neighbour row (or a source row) and no halo push: the kernel
+        // without the boundary-condition branches applies
+        sp.fastOnly = 1;
+        for (const TetRec& r : sp.recHost) {
+            for (int f = 0; f < 4; f++)
+                if (!(r.bc[f] == VT_PBC_NONBOUNDARY || r.bc[f] == VT_PBC_PERIODIC || r.bc[f] == VT_PBC_SOURCE)) sp.fastOnly = 0;
+            if (r.pushPeer[0] >= 0) sp.fastOnly = 0;
+            if (!sp.fastOnly) break;
+        }
+    }
     if (!ctx->workCounter) VT_CUDA(cudaMalloc(&ctx->workCounter, sizeof(unsigned long long)));
     BulkParams P;
     P.s = p;
@@ -488,20 +595,15 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     P.queue = ctx->workCounter;
     P.total = (long long)ctx->nOwned * p.nChunks;
     const int grid = (int)std::min<long long>(P.total, ctx->prop.multiProcessorCount);
+    const bool allFast = sp.fastOnly == 1;
 
-    auto launch = [&](auto kern) {
-        VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VT_CUDA(cudaMemsetAsync(ctx->workCounter, 0, sizeof(unsigned long long), ctx->stream));
-        VT_CUDA(cudaEventRecord(e0, ctx->stream));
-        kern<<<grid, kConsThreads + 32, smem, ctx->stream>>>(P);
-        VT_CUDA(cudaEventRecord(e1, ctx->stream));
-    };
-    if (kpt == 1) upwind ? launch(k_full_step_bulk<1, true>) : launch(k_full_step_bulk<1, false>);
-    else if (kpt == 2) upwind ? launch(k_full_step_bulk<2, true>) : launch(k_full_step_bulk<2, false>);
-    else if (kpt == 3) upwind ? launch(k_full_step_bulk<3, true>) : launch(k_full_step_bulk<3, false>);
-    else upwind ? launch(k_full_step_bulk<4, true>) : launch(k_full_step_bulk<4, false>);
+    if (wide) launch_cfg<2, 8>(ctx, P, upwind, allFast, grid, smem, e0, e1);
+    else if (kpt == 1) launch_cfg<1, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
+    else if (kpt == 2) launch_cfg<2, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
+    else if (kpt == 3) launch_cfg<3, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
+    else launch_cfg<4, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
     VT_CUDA(cudaGetLastError());
-    p.densSplit = kConsWarps;
+    p.densSplit = ncw;
     return true;
 }
 

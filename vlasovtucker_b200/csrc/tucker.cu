@@ -79,109 +79,309 @@ __device__ void mode_apply(const double* __restrict__ src, double* __restrict__ 
     __syncthreads();
 }
 
-// Gram matrix of the mode-k unfolding: G[i + n*j] = sum over the other two indices X(..i..) X(..j..)
-__device__ void gram(const double* __restrict__ X, const int d[3], int mode, double* __restrict__ G)
+// ---- Gram matrices of the three unfoldings, G_k = X_(k) X_(k)^T, accumulated from shared-memory
+// tiles.  Each thread owns a fixed set of (i <= j) entries (pair table in shared memory) and keeps
+// them in registers across tiles; G is written symmetric with leading dimension ld = n | 1 (odd, so
+// that both row and column walks are bank-conflict free in the eigen-solver).
+constexpr int kMaxPairsPerThread = (kMaxN * (kMaxN + 1) / 2 + kThreads - 1) / kThreads;   // 9
+
+struct GramWork {
+    double* tile;              // tileCap = (nmax | 1) * nmax doubles
+    int tileCap;
+    const unsigned short* pairs;   // pair q -> i | (j << 8), i <= j, for n = nmax (prefix valid for smaller n)
+};
+
+__device__ __forceinline__ int pair_count(int n) { return n * (n + 1) / 2; }
+
+// pairs are enumerated column by column: (0,0), (0,1), (1,1), (0,2), ... so the first n(n+1)/2
+// entries of the table built for nmax are exactly the pairs of any n <= nmax
+__device__ void build_pairs(unsigned short* pairs, int nmax)
 {
-    const int n = d[mode];
-    const int a = (mode + 1) % 3, b = (mode + 2) % 3;
-    const int stride[3] = {1, d[0], d[0] * d[1]};
-    for (int p = threadIdx.x; p < n * n; p += blockDim.x) {
-        const int i = p % n, j = p / n;
-        if (j < i) continue;
-        double s = 0.0;
-        for (int ib = 0; ib < d[b]; ib++)
-            for (int ia = 0; ia < d[a]; ia++) {
-                const int off = ia * stride[a] + ib * stride[b];
-                s += X[off + i * stride[mode]] * X[off + j * stride[mode]];
-            }
-        G[i + n * j] = s;
-        G[j + n * i] = s;
+    for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
+        const int base = j * (j + 1) / 2;
+        for (int i = 0; i <= j; i++) pairs[base + i] = (unsigned short)(i | (j << 8));
     }
     __syncthreads();
 }
 
-// Eigen-decomposition of the symmetric PSD n x n matrix in W (column-major, overwritten): one-sided
-// Jacobi W <- W J, V <- V J until the columns of W = G V are orthogonal; eigenvalue_j = |w_j|.
-// Round-robin ordering gives n/2 independent column pairs per round; one warp rotates one pair.
-__device__ void jacobi_eig(double* W, double* V, int n, double* lambda, int* order, int* flag)
+__device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode, double* __restrict__ G, const GramWork& gw)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for (int p = threadIdx.x; p < n * n; p += blockDim.x) V[p] = (p % n == p / n) ? 1.0 : 0.0;
-    __syncthreads();
-    const int m = (n + 1) & ~1;   // even number of players; index n (if odd) is a bye
-    for (int sweep = 0; sweep < 40; sweep++) {
-        if (threadIdx.x == 0) *flag = 0;
-        __syncthreads();
-        for (int round = 0; round < m - 1; round++) {
-            for (int pr = warp; pr < m / 2; pr += nwarps) {
-                int p, q;
-                if (pr == 0) {
-                    p = m - 1;
-                    q = round;
+    const int n = d[mode];
+    const int np = pair_count(n);
+    double acc[kMaxPairsPerThread];
+    int pi[kMaxPairsPerThread], pj[kMaxPairsPerThread];
+#pragma unroll
+    for (int k = 0; k < kMaxPairsPerThread; k++) {
+        acc[k] = 0.0;
+        const int q = threadIdx.x + k * kThreads;
+        const unsigned short pr = q < np ? gw.pairs[q] : 0;
+        pi[k] = pr & 255;
+        pj[k] = pr >> 8;
+    }
+    const int n0 = d[0], n1 = d[1], n2 = d[2], M = n0 * n1;
+    if (mode == 0 || mode == 1) {
+        // slabs A = X(:, :, i2), n0 x n1; mode 0: G += A A^T, mode 1: G += A^T A
+        const int ld = mode == 0 ? n0 : (n0 | 1);
+        for (int i2 = 0; i2 < n2; i2++) {
+            const double* slab = X + (size_t)i2 * M;
+            for (int e = threadIdx.x; e < M; e += blockDim.x) gw.tile[(e % n0) + ld * (e / n0)] = slab[e];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kMaxPairsPerThread; k++) {
+                if (threadIdx.x + k * kThreads >= np) break;
+                double s = acc[k];
+                if (mode == 0) {
+                    const double* a = gw.tile + pi[k];
+                    const double* b = gw.tile + pj[k];
+                    for (int c = 0; c < n1; c++) s = fma(a[ld * c], b[ld * c], s);
                 } else {
-                    p = (round + pr) % (m - 1);
-                    q = (round - pr + (m - 1)) % (m - 1);
+                    const double* a = gw.tile + ld * pi[k];
+                    const double* b = gw.tile + ld * pj[k];
+                    for (int r = 0; r < n0; r++) s = fma(a[r], b[r], s);
                 }
-                if (p >= n || q >= n) continue;
-                if (p > q) {
-                    const int t = p;
-                    p = q;
-                    q = t;
-                }
-                double a = 0, b = 0, g = 0;
-                for (int i = lane; i < n; i += 32) {
-                    const double x = W[i + n * p], y = W[i + n * q];
-                    a += x * x;
-                    b += y * y;
-                    g += x * y;
-                }
-                for (int o = 16; o > 0; o >>= 1) {
-                    a += __shfl_xor_sync(0xffffffffu, a, o);
-                    b += __shfl_xor_sync(0xffffffffu, b, o);
-                    g += __shfl_xor_sync(0xffffffffu, g, o);
-                }
-                if (g == 0.0 || fabs(g) <= 1e-15 * sqrt(a * b)) continue;
-                if (lane == 0) *flag = 1;
-                const double z = (b - a) / (2 * g);
-                const double t = (z >= 0 ? 1.0 : -1.0) / (fabs(z) + sqrt(1 + z * z));
-                const double cs = 1 / sqrt(1 + t * t), sn = cs * t;
-                for (int i = lane; i < n; i += 32) {
-                    const double x = W[i + n * p], y = W[i + n * q];
-                    W[i + n * p] = cs * x - sn * y;
-                    W[i + n * q] = sn * x + cs * y;
-                    const double vx = V[i + n * p], vy = V[i + n * q];
-                    V[i + n * p] = cs * vx - sn * vy;
-                    V[i + n * q] = sn * vx + cs * vy;
-                }
+                acc[k] = s;
             }
             __syncthreads();
         }
-        if (*flag == 0) break;
-        __syncthreads();
+    } else {
+        // X as an M x n2 matrix B (column a = plane a); G = B^T B over row chunks of Tr rows
+        const int ldmax = gw.tileCap / n2;                       // the chunk (ld x n2) has to fit the tile
+        const int rows = min(M, (ldmax & 1) ? ldmax : ldmax - 1);
+        const int ld = rows | 1;
+        for (int r0 = 0; r0 < M; r0 += rows) {
+            const int nr = min(rows, M - r0);
+            for (int e = threadIdx.x; e < nr * n2; e += blockDim.x) {
+                const int r = e % nr, a = e / nr;
+                gw.tile[r + ld * a] = X[(size_t)r0 + r + (size_t)M * a];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kMaxPairsPerThread; k++) {
+                if (threadIdx.x + k * kThreads >= np) break;
+                const double* a = gw.tile + ld * pi[k];
+                const double* b = gw.tile + ld * pj[k];
+                double s = acc[k];
+                for (int r = 0; r < nr; r++) s = fma(a[r], b[r], s);
+                acc[k] = s;
+            }
+            __syncthreads();
+        }
     }
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        double s = 0;
-        for (int i = 0; i < n; i++) s += W[i + n * j] * W[i + n * j];
-        lambda[j] = sqrt(s);
-    }
-    __syncthreads();
-    // descending order by rank counting (stable)
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        int rank = 0;
-        for (int i = 0; i < n; i++)
-            if (lambda[i] > lambda[j] || (lambda[i] == lambda[j] && i < j)) rank++;
-        order[rank] = j;
+    const int ldg = n | 1;
+#pragma unroll
+    for (int k = 0; k < kMaxPairsPerThread; k++) {
+        if (threadIdx.x + k * kThreads >= np) break;
+        G[pi[k] + ldg * pj[k]] = acc[k];
+        G[pj[k] + ldg * pi[k]] = acc[k];
     }
     __syncthreads();
 }
 
+__device__ __forceinline__ double wsum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Symmetric eigen-decomposition by one warp, in place: Householder tridiagonalisation followed by
+// the implicit QL iteration (the EISPACK tred2/tql2 pair in the form popularised by JAMA), inner
+// loops spread over the 32 lanes.  V (n x n, leading dimension ld) holds the matrix on entry and
+// the eigenvectors (columns) on exit; dv the eigenvalues (unordered), ev is work space.
+#define VV(i, j) V[(i) + ld * (j)]
+__device__ void eig_sym_warp(double* V, int n, int ld, double* dv, double* ev)
+{
+    const int lane = threadIdx.x & 31;
+    for (int j = lane; j < n; j += 32) dv[j] = VV(n - 1, j);
+    __syncwarp();
+    for (int i = n - 1; i > 0; i--) {
+        double part = 0.0;
+        for (int k = lane; k < i; k += 32) part += fabs(dv[k]);
+        const double scale = wsum(part);
+        double h = 0.0;
+        if (scale == 0.0) {
+            if (lane == 0) ev[i] = dv[i - 1];
+            __syncwarp();
+            for (int j = lane; j < i; j += 32) {
+                dv[j] = VV(i - 1, j);
+                VV(i, j) = 0.0;
+                VV(j, i) = 0.0;
+            }
+        } else {
+            part = 0.0;
+            for (int k = lane; k < i; k += 32) {
+                const double x = dv[k] / scale;
+                dv[k] = x;
+                part += x * x;
+            }
+            h = wsum(part);
+            __syncwarp();
+            const double f = dv[i - 1];
+            double g = sqrt(h);
+            if (f > 0) g = -g;
+            h -= f * g;
+            __syncwarp();
+            if (lane == 0) {
+                ev[i] = scale * g;
+                dv[i - 1] = f - g;
+            }
+            __syncwarp();
+            // e = A d on the leading i x i block (lower triangle valid), and store the Householder vector
+            for (int j = lane; j < i; j += 32) {
+                double s = 0.0;
+                for (int k = 0; k <= j; k++) s = fma(VV(j, k), dv[k], s);
+                for (int k = j + 1; k < i; k++) s = fma(VV(k, j), dv[k], s);
+                ev[j] = s;
+            }
+            __syncwarp();
+            for (int j = lane; j < i; j += 32) VV(j, i) = dv[j];
+            part = 0.0;
+            for (int j = lane; j < i; j += 32) {
+                const double x = ev[j] / h;
+                ev[j] = x;
+                part += x * dv[j];
+            }
+            const double hh = wsum(part) / (h + h);
+            __syncwarp();
+            for (int j = lane; j < i; j += 32) ev[j] -= hh * dv[j];
+            __syncwarp();
+            // rank-2 update of the lower triangle: row k, columns j <= k
+            for (int k = lane; k < i; k += 32) {
+                const double ek = ev[k], dk = dv[k];
+                for (int j = 0; j <= k; j++) VV(k, j) -= dv[j] * ek + ev[j] * dk;
+            }
+            __syncwarp();
+            for (int j = lane; j < i; j += 32) {
+                dv[j] = VV(i - 1, j);
+                VV(i, j) = 0.0;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) dv[i] = h;
+        __syncwarp();
+    }
+    // accumulate the transformations
+    for (int i = 0; i < n - 1; i++) {
+        if (lane == 0) {
+            VV(n - 1, i) = VV(i, i);
+            VV(i, i) = 1.0;
+        }
+        __syncwarp();
+        const double h = dv[i + 1];
+        if (h != 0.0) {
+            for (int k = lane; k <= i; k += 32) dv[k] = VV(k, i + 1) / h;
+            __syncwarp();
+            for (int j = lane; j <= i; j += 32) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g = fma(VV(k, i + 1), VV(k, j), g);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * dv[k];
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k <= i; k += 32) VV(k, i + 1) = 0.0;
+        __syncwarp();
+    }
+    for (int j = lane; j < n; j += 32) {
+        dv[j] = VV(n - 1, j);
+        VV(n - 1, j) = 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        VV(n - 1, n - 1) = 1.0;
+        ev[0] = 0.0;
+    }
+    __syncwarp();
+    // implicit QL
+    {
+        const double t0 = (1 + lane < n) ? ev[1 + lane] : 0.0, t1 = (33 + lane < n) ? ev[33 + lane] : 0.0;
+        __syncwarp();
+        if (1 + lane < n) ev[lane] = t0;
+        if (33 + lane < n) ev[32 + lane] = t1;
+    }
+    __syncwarp();
+    if (lane == 0) ev[n - 1] = 0.0;
+    __syncwarp();
+    double f = 0.0, tst1 = 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        tst1 = fmax(tst1, fabs(dv[l]) + fabs(ev[l]));
+        int m = l;
+        while (m < n) {
+            if (fabs(ev[m]) <= eps * tst1) break;
+            m++;
+        }
+        if (m > l) {
+            int iter = 0;
+            do {
+                iter++;
+                double g = dv[l];
+                double p = (dv[l + 1] - g) / (2.0 * ev[l]);
+                double r = hypot(p, 1.0);
+                if (p < 0) r = -r;
+                const double el = ev[l];
+                const double dl = el / (p + r), dl1 = el * (p + r);
+                double h = g - dl;
+                __syncwarp();
+                if (lane == 0) {
+                    dv[l] = dl;
+                    dv[l + 1] = dl1;
+                }
+                for (int i = l + 2 + lane; i < n; i += 32) dv[i] -= h;
+                __syncwarp();
+                f += h;
+                p = dv[m];
+                double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
+                const double el1 = ev[l + 1];
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2;
+                    c2 = c;
+                    s2 = s;
+                    const double ei = ev[i], di = dv[i];
+                    g = c * ei;
+                    h = c * p;
+                    r = hypot(p, ei);
+                    s = ei / r;
+                    c = p / r;
+                    p = c * di - s * g;
+                    __syncwarp();
+                    if (lane == 0) {
+                        // e[i+1] = s_prev * r, d[i+1] = h + s (c g + s d[i])
+                        ev[i + 1] = s2 * r;
+                        dv[i + 1] = h + s * (c * g + s * di);
+                    }
+                    for (int k = lane; k < n; k += 32) {
+                        const double vh = VV(k, i + 1), vl = VV(k, i);
+                        VV(k, i + 1) = s * vl + c * vh;
+                        VV(k, i) = c * vl - s * vh;
+                    }
+                    __syncwarp();
+                }
+                p = -s * s2 * c3 * el1 * ev[l] / dl1;
+                __syncwarp();
+                if (lane == 0) {
+                    ev[l] = s * p;
+                    dv[l] = c * p;
+                }
+                __syncwarp();
+            } while (fabs(ev[l]) > eps * tst1 && iter < 60);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            dv[l] = dv[l] + f;
+            ev[l] = 0.0;
+        }
+        __syncwarp();
+    }
+}
+#undef VV
+
 struct TruncWork {
-    double* G;        // [kMaxN*kMaxN] shared
-    double* V;        // [kMaxN*kMaxN] shared
-    double* lambda;   // [kMaxN] shared
-    int* order;       // [kMaxN] shared
-    int* flag;        // shared
+    double* G[3];     // shared: Gram matrices -> eigenvectors, leading dimension n_k | 1
+    double* dv;       // [3][kMaxN] shared: eigenvalues
+    double* ev;       // [3][kMaxN] shared: work
+    int* order;       // [3][kMaxN] shared: descending order
     int* rsel;        // [3] shared: selected ranks
+    GramWork gw;
 };
 
 // Truncated HOSVD of the dense tensor X (dims d).  Writes the factors to Uout[k] (leading dimension
@@ -190,32 +390,48 @@ struct TruncWork {
 __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int rmax, const int rcap[3], double* const Uout[3],
                                double* coreOut, double* W1, double* W2, const TruncWork& w)
 {
-    for (int k = 0; k < 3; k++) {
-        const int n = d[k];
-        gram(X, d, k, w.G);
-        jacobi_eig(w.G, w.V, n, w.lambda, w.order, w.flag);
-        if (threadIdx.x == 0) {
-            // sigma_j = sqrt(lambda_j); |sigma|^2 = sum lambda_j              (tucker.cpp:450)
-            double s2 = 0;
-            for (int j = 0; j < n; j++) s2 += w.lambda[j];
-            const double thr = eps * sqrt(s2) / sqrt(3.0);
-            int r = 0;
-            const int cap = min(rmax, rcap[k]);
-            for (int j = 0; j < n; j++) {
-                const double sig = sqrt(fmax(w.lambda[w.order[j]], 0.0));
-                if (r == 0 || (sig > thr && r < cap)) r++;   // sorted: a prefix is kept       (tucker.cpp:454-460)
-                else break;
-            }
-            w.rsel[k] = r;
+    for (int k = 0; k < 3; k++) gram_mode(X, d, k, w.G[k], w.gw);
+    const int warp = threadIdx.x >> 5;
+    if (warp < 3) eig_sym_warp(w.G[warp], d[warp], d[warp] | 1, w.dv + warp * kMaxN, w.ev + warp * kMaxN);
+    __syncthreads();
+    // descending order by rank counting (stable); eigenvalues of a Gram matrix are >= 0 up to rounding
+    for (int q = threadIdx.x; q < 3 * kMaxN; q += blockDim.x) {
+        const int k = q / kMaxN, j = q % kMaxN;
+        if (j >= d[k]) continue;
+        const double* lam = w.dv + k * kMaxN;
+        int rank = 0;
+        for (int i = 0; i < d[k]; i++)
+            if (lam[i] > lam[j] || (lam[i] == lam[j] && i < j)) rank++;
+        w.order[k * kMaxN + rank] = j;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x, n = d[k];
+        const double* lam = w.dv + k * kMaxN;
+        const int* ord = w.order + k * kMaxN;
+        // sigma_j = sqrt(lambda_j); |sigma|^2 = sum lambda_j              (tucker.cpp:450)
+        double s2 = 0;
+        for (int j = 0; j < n; j++) s2 += fmax(lam[j], 0.0);
+        const double thr = eps * sqrt(s2) / sqrt(3.0);
+        int r = 0;
+        const int cap = min(rmax, rcap[k]);
+        for (int j = 0; j < n; j++) {
+            const double sig = sqrt(fmax(lam[ord[j]], 0.0));
+            if (r == 0 || (sig > thr && r < cap)) r++;   // sorted: a prefix is kept       (tucker.cpp:454-460)
+            else break;
         }
-        __syncthreads();
-        const int r = w.rsel[k];
+        w.rsel[k] = r;
+    }
+    __syncthreads();
+    for (int k = 0; k < 3; k++) {
+        const int n = d[k], r = w.rsel[k], ld = n | 1;
+        const int* ord = w.order + k * kMaxN;
         for (int p = threadIdx.x; p < n * r; p += blockDim.x) {
             const int i = p % n, j = p / n;
-            Uout[k][i + n * j] = w.V[i + n * w.order[j]];
+            Uout[k][i + n * j] = w.G[k][i + ld * ord[j]];
         }
-        __syncthreads();
     }
+    __syncthreads();
     // core = X x1 U0^T x2 U1^T x3 U2^T
     int dd[3] = {d[0], d[1], d[2]};
     mode_apply(X, W1, dd, 0, Uout[0], d[0], w.rsel[0], true);
@@ -275,17 +491,25 @@ __device__ void slot_ptrs(double* base, const TuckerParams& P, double*& core, do
 
 __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
 {
-    extern __shared__ double sDyn[];   // 2 * nmax^2 doubles: Gram matrix and eigenvectors
+    extern __shared__ double sDyn[];   // 3 Gram/eigenvector matrices + one staging tile, (nmax|1)*nmax doubles each
     const int nmaxS = max(P.n[0], max(P.n[1], P.n[2]));
-    double* sG = sDyn;
-    double* sV = sDyn + nmaxS * nmaxS;
-    __shared__ double sLambda[kMaxN];
-    __shared__ int sOrder[kMaxN];
-    __shared__ int sFlag;
+    const int matElems = (nmaxS | 1) * nmaxS;
+    __shared__ double sDv[3 * kMaxN], sEv[3 * kMaxN];
+    __shared__ int sOrder[3 * kMaxN];
+    __shared__ unsigned short sPairs[kMaxN * (kMaxN + 1) / 2];
     __shared__ int sR[3];
     __shared__ double sRed[kThreads / 32][5];
     __shared__ TetRec rec;
-    TruncWork w{sG, sV, sLambda, sOrder, &sFlag, sR};
+    TruncWork w;
+    for (int k = 0; k < 3; k++) w.G[k] = sDyn + (size_t)k * matElems;
+    w.dv = sDv;
+    w.ev = sEv;
+    w.order = sOrder;
+    w.rsel = sR;
+    w.gw.tile = sDyn + (size_t)3 * matElems;
+    w.gw.tileCap = matElems;
+    w.gw.pairs = sPairs;
+    build_pairs(sPairs, nmaxS);
 
     const int d[3] = {P.n[0], P.n[1], P.n[2]};
     const int N = P.N;
@@ -492,9 +716,9 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     if (ctx->nOwned == 0) return;
     const int grid = std::min(ctx->nOwned, ts.scratchCTAs);
     const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
-    const size_t smem = 2 * (size_t)nmax * nmax * sizeof(double);
-    if (smem > 40 * 1024)
-        VT_CUDA(cudaFuncSetAttribute(k_tucker, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kMaxN * kMaxN * (int)sizeof(double)));
+    const size_t smem = 4 * (size_t)(nmax | 1) * nmax * sizeof(double);
+    if (smem > 32 * 1024)
+        VT_CUDA(cudaFuncSetAttribute(k_tucker, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
     k_tucker<<<grid, kThreads, smem, ctx->stream>>>(P);
     ctx->launches++;
     VT_CUDA(cudaGetLastError());

@@ -134,6 +134,7 @@ void rebuild_tet_records(vt_ctx* ctx, vt::Species& sp)
     sp.recHost.assign(n, vt::TetRec());
     sp.wallEntities.clear();
     sp.danglingFaces = 0;
+    sp.fastOnly = -1;
     std::map<int, int> slotOf;
     for (int p = 0; p < n; p++) {
         const int t = ctx->order[p];

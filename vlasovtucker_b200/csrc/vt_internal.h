@@ -80,6 +80,7 @@ struct Species {
     std::vector<uint8_t> bcType, collect;
     std::vector<int32_t> sourceId;
     int danglingFaces = 0;            // boundary faces with neither neighbour nor particle BC
+    int fastOnly = -1;                // 1: no tet needs the boundary/halo branches; -1: not evaluated
     // halo (multi-GPU): peers' ping-pong buffers opened through CUDA IPC
     int nPeers = 0;
     double* peerF[kMaxPeers][2] = {};
@@ -124,7 +125,8 @@ struct vt_ctx {
     double* pinned = nullptr;  // pinned host staging
     size_t pinnedBytes = 0;
 
-    int chunkPlanes = 0, brickTets = 0, variant = 0;
+    int chunkPlanes = 0, brickTets = 0;
+    int variant = 64;   // vt_step_config bits; 64 = choose the step kernel from the velocity grid
     unsigned long long* workCounter = nullptr;   // device: head of the persistent kernel's work queue
 
     vt::PoissonData* poisson = nullptr;
