@@ -442,6 +442,15 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
     }
 }
 
+// Boundary / halo-push tets are a small minority of a partition: keeping their code out of line
+// leaves the all-interior path with the registers it has in the ALLFAST kernel.
+template <int KPT, bool UPWIND, int NCW>
+__device__ __noinline__ void item_compute_generic(const BulkParams& P, const ConsRings& R, const ItemHdr& cur, const TetRec& rec,
+                                                  uint32_t& cOwn, uint32_t& cNbr, const Column (&col)[KPT])
+{
+    item_compute<KPT, UPWIND, true, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+}
+
 template <int KPT, bool UPWIND, int NCW, bool ALLFAST>
 __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkParams P)
 {
@@ -525,7 +534,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
             const bool fast = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]) &&
                               rec.pushPeer[0] < 0;
             if (fast) item_compute<KPT, UPWIND, false, NCW>(P, R, cur, rec, cOwn, cNbr, col);
-            else item_compute<KPT, UPWIND, true, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+            else item_compute_generic<KPT, UPWIND, NCW>(P, R, cur, rec, cOwn, cNbr, col);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.itemEmpty + cItem.slot);

@@ -56,25 +56,51 @@ struct Dims {
 
 // dst (dims with dim[mode] -> rows) = src x_mode M.  M is addressed M[out + ldm*in] (transpose=false,
 // an "rows x n_mode" matrix stored column-major) or M[in + ldm*out] (transpose=true: apply U^T).
+// Ms: shared staging for M (>= rowsOut * din[mode] doubles).  A thread takes one fibre of the
+// contracted mode and a block of kQB output rows: every element read from src feeds kQB FMAs whose
+// matrix operands are shared-memory broadcasts; consecutive threads take consecutive fibres, which
+// are consecutive i0 (coalesced) for modes 1 and 2.
+constexpr int kQB = 8;
 __device__ void mode_apply(const double* __restrict__ src, double* __restrict__ dst, const int din[3], int mode,
-                           const double* __restrict__ M, int ldm, int rowsOut, bool transpose)
+                           const double* __restrict__ M, int ldm, int rowsOut, bool transpose, double* __restrict__ Ms)
 {
-    int dout[3] = {din[0], din[1], din[2]};
-    dout[mode] = rowsOut;
-    const int total = dout[0] * dout[1] * dout[2];
+    const int K = din[mode];
+    const int QS = (rowsOut + kQB - 1) / kQB * kQB;   // padded row count: Ms[k * QS + q]
+    for (int e = threadIdx.x; e < QS * K; e += blockDim.x) {
+        const int q = e % QS, k = e / QS;
+        Ms[e] = q < rowsOut ? (transpose ? M[k + ldm * q] : M[q + ldm * k]) : 0.0;
+    }
+    __syncthreads();
+    const int nFib = din[0] * din[1] * din[2] / K;
+    const int nQB = QS / kQB;
     const int strideIn = mode == 0 ? 1 : (mode == 1 ? din[0] : din[0] * din[1]);
-    for (int o = threadIdx.x; o < total; o += blockDim.x) {
-        const int o0 = o % dout[0], o1 = (o / dout[0]) % dout[1], o2 = o / (dout[0] * dout[1]);
-        int i[3] = {o0, o1, o2};
-        const int q = i[mode];
-        i[mode] = 0;
-        const int base = i[0] + din[0] * (i[1] + din[1] * i[2]);
-        double s = 0.0;
-        for (int k = 0; k < din[mode]; k++) {
-            const double m = transpose ? M[k + ldm * q] : M[q + ldm * k];
-            s += m * src[base + k * strideIn];
+    const int strideOut = mode == 0 ? 1 : strideIn;
+    for (int w = threadIdx.x; w < nFib * nQB; w += blockDim.x) {
+        const int fib = w % nFib, q0 = (w / nFib) * kQB;
+        int baseIn, baseOut;
+        if (mode == 0) {
+            baseIn = fib * K;
+            baseOut = fib * rowsOut;
+        } else if (mode == 1) {
+            const int i0 = fib % din[0], i2 = fib / din[0];
+            baseIn = i0 + din[0] * K * i2;
+            baseOut = i0 + din[0] * rowsOut * i2;
+        } else {
+            baseIn = fib;
+            baseOut = fib;
         }
-        dst[o] = s;
+        double acc[kQB];
+#pragma unroll
+        for (int b = 0; b < kQB; b++) acc[b] = 0.0;
+        const double* mrow = Ms + q0;
+        for (int k = 0; k < K; k++) {
+            const double x = src[baseIn + k * strideIn];
+#pragma unroll
+            for (int b = 0; b < kQB; b++) acc[b] = fma(mrow[k * QS + b], x, acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < kQB; b++)
+            if (q0 + b < rowsOut) dst[baseOut + (q0 + b) * strideOut] = acc[b];
     }
     __syncthreads();
 }
@@ -433,24 +459,26 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
     }
     __syncthreads();
     // core = X x1 U0^T x2 U1^T x3 U2^T
+    // (mode products commute: the big coalesced contraction goes first, the strided mode-0 one last
+    // on the smallest tensor)
     int dd[3] = {d[0], d[1], d[2]};
-    mode_apply(X, W1, dd, 0, Uout[0], d[0], w.rsel[0], true);
-    dd[0] = w.rsel[0];
-    mode_apply(W1, W2, dd, 1, Uout[1], d[1], w.rsel[1], true);
+    mode_apply(X, W1, dd, 2, Uout[2], d[2], w.rsel[2], true, w.gw.tile);
+    dd[2] = w.rsel[2];
+    mode_apply(W1, W2, dd, 1, Uout[1], d[1], w.rsel[1], true, w.gw.tile);
     dd[1] = w.rsel[1];
-    mode_apply(W2, coreOut, dd, 2, Uout[2], d[2], w.rsel[2], true);
+    mode_apply(W2, coreOut, dd, 0, Uout[0], d[0], w.rsel[0], true, w.gw.tile);
 }
 
 // dense = core x1 U0 x2 U1 x3 U2
 __device__ void reconstruct(const double* core, const int r[3], double* const U[3], const int d[3], double* out, double* W1,
-                            double* W2)
+                            double* W2, double* Ms)
 {
     int dd[3] = {r[0], r[1], r[2]};
-    mode_apply(core, W1, dd, 0, U[0], d[0], d[0], false);
+    mode_apply(core, W1, dd, 0, U[0], d[0], d[0], false, Ms);
     dd[0] = d[0];
-    mode_apply(W1, W2, dd, 1, U[1], d[1], d[1], false);
+    mode_apply(W1, W2, dd, 1, U[1], d[1], d[1], false, Ms);
     dd[1] = d[1];
-    mode_apply(W2, out, dd, 2, U[2], d[2], d[2], false);
+    mode_apply(W2, out, dd, 2, U[2], d[2], d[2], false, Ms);
 }
 
 struct TuckerParams {
@@ -507,7 +535,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
     w.order = sOrder;
     w.rsel = sR;
     w.gw.tile = sDyn + (size_t)3 * matElems;
-    w.gw.tileCap = matElems;
+    w.gw.tileCap = max(nmaxS | 1, (nmaxS + kQB - 1) / kQB * kQB) * nmaxS;   // also stages a padded factor (mode_apply)
     w.gw.pairs = sPairs;
     build_pairs(sPairs, nmaxS);
 
@@ -528,7 +556,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             double *core, *U[3];
             slot_ptrs(const_cast<double*>(P.in) + (size_t)t * P.slot, P, core, U);
             const int r[3] = {P.rin[3 * t], P.rin[3 * t + 1], P.rin[3 * t + 2]};
-            reconstruct(core, r, U, d, P.denseOut + (size_t)t * N, W1, W2);
+            reconstruct(core, r, U, d, P.denseOut + (size_t)t * N, W1, W2, w.gw.tile);
             continue;
         }
         if (P.mode == 1) {   // compress dense input into the slot (initial condition: exact, precision 0)
@@ -560,7 +588,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
                 __syncthreads();
                 hosvd_truncate(A, d, P.epsAbs, 6, fullcap, Uw, coreW, W1, W2, w);
                 const int r[3] = {sR[0], sR[1], sR[2]};
-                reconstruct(coreW, r, Uw, d, const_cast<double*>(P.vnabs) + ((size_t)t * 4 + f) * N, W1, W2);
+                reconstruct(coreW, r, Uw, d, const_cast<double*>(P.vnabs) + ((size_t)t * 4 + f) * N, W1, W2, w.gw.tile);
             }
             continue;
         }
@@ -570,7 +598,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             double *core, *U[3];
             slot_ptrs(const_cast<double*>(P.in) + (size_t)t * P.slot, P, core, U);
             const int r[3] = {P.rin[3 * t], P.rin[3 * t + 1], P.rin[3 * t + 2]};
-            reconstruct(core, r, U, d, A, W1, W2);
+            reconstruct(core, r, U, d, A, W1, W2, w.gw.tile);
         }
         for (int e = threadIdx.x; e < N; e += blockDim.x) RHS[e] = 0.0;
         __syncthreads();
@@ -588,7 +616,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
                 double *core, *U[3];
                 slot_ptrs(const_cast<double*>(P.in) + (size_t)nb * P.slot, P, core, U);
                 const int r[3] = {P.rin[3 * nb], P.rin[3 * nb + 1], P.rin[3 * nb + 2]};
-                reconstruct(core, r, U, d, B, W1, W2);
+                reconstruct(core, r, U, d, B, W1, W2, w.gw.tile);
             }
             const double coef = rec.coef[f];
             const double* va = P.vnabs + ((size_t)t * 4 + f) * N;
@@ -611,7 +639,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             // rhs.Compress(comprErr, maxRank)                                           solver.cpp:182
             hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);
             const int r[3] = {sR[0], sR[1], sR[2]};
-            reconstruct(coreW, r, Uw, d, RHS, W1, W2);
+            reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile);
         }
         // acceleration: rhs -= (q/m)(E_k+ext_k) D_k f, D = zero-outside central difference       solver.cpp:187-200, 348-361
         {
@@ -633,7 +661,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             __syncthreads();
             hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);   // solver.cpp:199
             const int r[3] = {sR[0], sR[1], sR[2]};
-            reconstruct(coreW, r, Uw, d, RHS, W1, W2);
+            reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile);
         }
         // pdf += dt*rhs ; pdf.Compress                                                         solver.cpp:207-210
         for (int e = threadIdx.x; e < N; e += blockDim.x) B[e] = A[e] + P.dt * RHS[e];
@@ -644,7 +672,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             hosvd_truncate(B, d, P.eps, P.maxRank, P.rcap, U, core, W1, W2, w);
             if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
             const int r[3] = {sR[0], sR[1], sR[2]};
-            reconstruct(core, r, U, d, B, W1, W2);   // Density() sums the rounded tensor (particle_data.cpp:99)
+            reconstruct(core, r, U, d, B, W1, W2, w.gw.tile);   // Density() sums the rounded tensor (particle_data.cpp:99)
         }
         double acc = 0.0;
         for (int e = threadIdx.x; e < N; e += blockDim.x) acc += B[e];
@@ -716,7 +744,7 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     if (ctx->nOwned == 0) return;
     const int grid = std::min(ctx->nOwned, ts.scratchCTAs);
     const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
-    const size_t smem = 4 * (size_t)(nmax | 1) * nmax * sizeof(double);
+    const size_t smem = (3 * (size_t)(nmax | 1) + std::max(nmax | 1, (nmax + kQB - 1) / kQB * kQB)) * nmax * sizeof(double);
     if (smem > 32 * 1024)
         VT_CUDA(cudaFuncSetAttribute(k_tucker, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
     k_tucker<<<grid, kThreads, smem, ctx->stream>>>(P);
