@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_tucker_gpu.py -x -q -m gpu 2>&1 | tail -4 | cut -c1-300
+VT_TUCKER_PROFILE=1 timeout 600 python scripts/tucker_bench.py --steps 2 2>&1 | grep -E "vt_step_tucker|case" | awk 'NR%3!=2' | cut -c1-330 | tee gpurun_out/tucker_phases.log

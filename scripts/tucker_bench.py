@@ -47,7 +47,10 @@ def run(hexes, nv, eps, max_rank, steps):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--case", type=int, default=-1, help="run only this case (0, 1 or 2)")
     a = ap.parse_args()
-    run((8, 8, 8), 11, 1e-6, 0, a.steps)
-    run((8, 8, 8), 32, 1e-6, 8, max(1, a.steps // 2))
-    run((4, 4, 4), 48, 1e-6, 8, max(1, a.steps // 2))
+    cases = [((8, 8, 8), 11, 1e-6, 0, a.steps), ((8, 8, 8), 32, 1e-6, 8, max(1, a.steps // 2)),
+             ((4, 4, 4), 48, 1e-6, 8, max(1, a.steps // 2))]
+    for i, c in enumerate(cases):
+        if a.case < 0 or a.case == i:
+            run(*c)

@@ -34,7 +34,9 @@ struct TuckerState {
     size_t coreCap, slot;        // doubles per tet: core, whole slot (core + 3 factors)
     double* buf[2] = {nullptr, nullptr};   // compressed state, ping-pong
     int* ranks[2] = {nullptr, nullptr};    // 3 per tet
-    double* vnabs = nullptr;     // rank-<=6 reconstruction of |v.n|, 4 x N per owned tet (solver.cpp:282)
+    double* vnabs = nullptr;     // |v.n| per face as rank-<=6 Tucker tensors (solver.cpp:282): 4 slots per owned tet
+    int* vnabsRanks = nullptr;   // 3 per (tet, face)
+    size_t vslot = 0;            // doubles per slot: 6^3 core + 6 (n0 + n1 + n2)
     double* scratch = nullptr;   // per-CTA dense work space
     int scratchCTAs = 0;
     double comprErr = 1e-10;
@@ -408,6 +410,7 @@ struct TruncWork {
     int* order;       // [3][kMaxN] shared: descending order
     int* rsel;        // [3] shared: selected ranks
     GramWork gw;
+    long long* prof;  // optional phase timers (thread 0 of CTA 0): gram, eig, select, project, reconstruct, flux, derivative
 };
 
 // Truncated HOSVD of the dense tensor X (dims d).  Writes the factors to Uout[k] (leading dimension
@@ -416,10 +419,15 @@ struct TruncWork {
 __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int rmax, const int rcap[3], double* const Uout[3],
                                double* coreOut, double* W1, double* W2, const TruncWork& w)
 {
+    long long t0 = clock64();
     for (int k = 0; k < 3; k++) gram_mode(X, d, k, w.G[k], w.gw);
+    long long t1 = clock64();
+    if (w.prof) w.prof[0] += t1 - t0;
     const int warp = threadIdx.x >> 5;
     if (warp < 3) eig_sym_warp(w.G[warp], d[warp], d[warp] | 1, w.dv + warp * kMaxN, w.ev + warp * kMaxN);
     __syncthreads();
+    t0 = clock64();
+    if (w.prof) w.prof[1] += t0 - t1;
     // descending order by rank counting (stable); eigenvalues of a Gram matrix are >= 0 up to rounding
     for (int q = threadIdx.x; q < 3 * kMaxN; q += blockDim.x) {
         const int k = q / kMaxN, j = q % kMaxN;
@@ -459,6 +467,8 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
     }
     __syncthreads();
     // core = X x1 U0^T x2 U1^T x3 U2^T
+    t1 = clock64();
+    if (w.prof) w.prof[2] += t1 - t0;
     // (mode products commute: the big coalesced contraction goes first, the strided mode-0 one last
     // on the smallest tensor)
     int dd[3] = {d[0], d[1], d[2]};
@@ -467,18 +477,21 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
     mode_apply(W1, W2, dd, 1, Uout[1], d[1], w.rsel[1], true, w.gw.tile);
     dd[1] = w.rsel[1];
     mode_apply(W2, coreOut, dd, 0, Uout[0], d[0], w.rsel[0], true, w.gw.tile);
+    if (w.prof) w.prof[3] += clock64() - t1;
 }
 
 // dense = core x1 U0 x2 U1 x3 U2
 __device__ void reconstruct(const double* core, const int r[3], double* const U[3], const int d[3], double* out, double* W1,
-                            double* W2, double* Ms)
+                            double* W2, double* Ms, long long* prof = nullptr)
 {
+    const long long t0 = clock64();
     int dd[3] = {r[0], r[1], r[2]};
     mode_apply(core, W1, dd, 0, U[0], d[0], d[0], false, Ms);
     dd[0] = d[0];
     mode_apply(W1, W2, dd, 1, U[1], d[1], d[1], false, Ms);
     dd[1] = d[1];
     mode_apply(W2, out, dd, 2, U[2], d[2], d[2], false, Ms);
+    if (prof) prof[4] += clock64() - t0;
 }
 
 struct TuckerParams {
@@ -492,7 +505,9 @@ struct TuckerParams {
     int* rout;
     const TetRec* rec;
     const double* E;
-    const double* vnabs;   // [nOwned][4][N]
+    double* vnabs;         // [nOwned][4][vslot]: core 6^3, then U0 (n0 x 6), U1, U2
+    int* vnabsRanks;       // [nOwned][4][3]
+    size_t vslot;
     const double* src;     // dense source PDFs (Source BC), rows of N
     double* density;
     double* wall;
@@ -507,6 +522,7 @@ struct TuckerParams {
     int first;
     int mode;                // 0 step, 1 compress dense input, 2 reconstruct, 3 |v.n| tables
     double epsAbs;           // mode 3: compression error for |v.n| (rank cap 6)
+    long long* prof;         // optional: 8 phase timers in clock cycles (VT_TUCKER_PROFILE)
 };
 
 __device__ void slot_ptrs(double* base, const TuckerParams& P, double*& core, double* U[3])
@@ -538,6 +554,10 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
     w.gw.tileCap = max(nmaxS | 1, (nmaxS + kQB - 1) / kQB * kQB) * nmaxS;   // also stages a padded factor (mode_apply)
     w.gw.pairs = sPairs;
     build_pairs(sPairs, nmaxS);
+    __shared__ long long sProf[8];
+    if (threadIdx.x < 8) sProf[threadIdx.x] = 0;
+    w.prof = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? sProf : nullptr;
+    const long long tKernel = clock64();
 
     const int d[3] = {P.n[0], P.n[1], P.n[2]};
     const int N = P.N;
@@ -556,7 +576,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             double *core, *U[3];
             slot_ptrs(const_cast<double*>(P.in) + (size_t)t * P.slot, P, core, U);
             const int r[3] = {P.rin[3 * t], P.rin[3 * t + 1], P.rin[3 * t + 2]};
-            reconstruct(core, r, U, d, P.denseOut + (size_t)t * N, W1, W2, w.gw.tile);
+            reconstruct(core, r, U, d, P.denseOut + (size_t)t * N, W1, W2, w.gw.tile, w.prof);
             continue;
         }
         if (P.mode == 1) {   // compress dense input into the slot (initial condition: exact, precision 0)
@@ -586,9 +606,12 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
                     A[e] = fabs(rec.nrm[f][0] * v0 + rec.nrm[f][1] * v1 + rec.nrm[f][2] * v2);
                 }
                 __syncthreads();
-                hosvd_truncate(A, d, P.epsAbs, 6, fullcap, Uw, coreW, W1, W2, w);
-                const int r[3] = {sR[0], sR[1], sR[2]};
-                reconstruct(coreW, r, Uw, d, const_cast<double*>(P.vnabs) + ((size_t)t * 4 + f) * N, W1, W2, w.gw.tile);
+                double* vs = P.vnabs + ((size_t)t * 4 + f) * P.vslot;
+                double* Uv[3] = {vs + 216, vs + 216 + 6 * d[0], vs + 216 + 6 * (d[0] + d[1])};
+                const int cap6[3] = {min(6, d[0]), min(6, d[1]), min(6, d[2])};
+                hosvd_truncate(A, d, P.epsAbs, 6, cap6, Uv, vs, W1, W2, w);
+                if (threadIdx.x < 3) P.vnabsRanks[((size_t)t * 4 + f) * 3 + threadIdx.x] = sR[threadIdx.x];
+                __syncthreads();
             }
             continue;
         }
@@ -598,7 +621,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             double *core, *U[3];
             slot_ptrs(const_cast<double*>(P.in) + (size_t)t * P.slot, P, core, U);
             const int r[3] = {P.rin[3 * t], P.rin[3 * t + 1], P.rin[3 * t + 2]};
-            reconstruct(core, r, U, d, A, W1, W2, w.gw.tile);
+            reconstruct(core, r, U, d, A, W1, W2, w.gw.tile, w.prof);
         }
         for (int e = threadIdx.x; e < N; e += blockDim.x) RHS[e] = 0.0;
         __syncthreads();
@@ -616,10 +639,19 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
                 double *core, *U[3];
                 slot_ptrs(const_cast<double*>(P.in) + (size_t)nb * P.slot, P, core, U);
                 const int r[3] = {P.rin[3 * nb], P.rin[3 * nb + 1], P.rin[3 * nb + 2]};
-                reconstruct(core, r, U, d, B, W1, W2, w.gw.tile);
+                reconstruct(core, r, U, d, B, W1, W2, w.gw.tile, w.prof);
             }
             const double coef = rec.coef[f];
-            const double* va = P.vnabs + ((size_t)t * 4 + f) * N;
+            // |v.n| of this face from its rank-<=6 factors (coreW is free until the rounding below)
+            {
+                double* vs = P.vnabs + ((size_t)t * 4 + f) * P.vslot;
+                double* Uv[3] = {vs + 216, vs + 216 + 6 * d[0], vs + 216 + 6 * (d[0] + d[1])};
+                const int* vr = P.vnabsRanks + ((size_t)t * 4 + f) * 3;
+                const int r[3] = {vr[0], vr[1], vr[2]};
+                reconstruct(vs, r, Uv, d, coreW, W1, W2, w.gw.tile, w.prof);
+            }
+            const double* va = coreW;
+            const long long tFlux = clock64();
             for (int e = threadIdx.x; e < N; e += blockDim.x) {
                 const int i0 = e % d[0], i1 = (e / d[0]) % d[1], i2 = e / (d[0] * d[1]);
                 const double v0 = __dadd_rn(P.vmin[0], __dmul_rn((double)i0, P.step[0]));
@@ -636,16 +668,18 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
                 RHS[e] = RHS[e] - coef * flux;                                        // solver.cpp:168
             }
             __syncthreads();
+            if (w.prof) w.prof[5] += clock64() - tFlux;
             // rhs.Compress(comprErr, maxRank)                                           solver.cpp:182
             hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);
             const int r[3] = {sR[0], sR[1], sR[2]};
-            reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile);
+            reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile, w.prof);
         }
         // acceleration: rhs -= (q/m)(E_k+ext_k) D_k f, D = zero-outside central difference       solver.cpp:187-200, 348-361
         {
             double g[3];
             for (int k = 0; k < 3; k++) g[k] = (P.qm * (P.E[3 * (size_t)t + k] + P.ext[k])) * P.inv2h[k];
             const int stride[3] = {1, d[0], d[0] * d[1]};
+            const long long tDer = clock64();
             for (int e = threadIdx.x; e < N; e += blockDim.x) {
                 const int i[3] = {e % d[0], (e / d[0]) % d[1], e / (d[0] * d[1])};
                 double r = RHS[e];
@@ -659,9 +693,10 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             __syncthreads();
             for (int e = threadIdx.x; e < N; e += blockDim.x) RHS[e] = W1[e];
             __syncthreads();
+            if (w.prof) w.prof[6] += clock64() - tDer;
             hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);   // solver.cpp:199
             const int r[3] = {sR[0], sR[1], sR[2]};
-            reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile);
+            reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile, w.prof);
         }
         // pdf += dt*rhs ; pdf.Compress                                                         solver.cpp:207-210
         for (int e = threadIdx.x; e < N; e += blockDim.x) B[e] = A[e] + P.dt * RHS[e];
@@ -672,7 +707,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             hosvd_truncate(B, d, P.eps, P.maxRank, P.rcap, U, core, W1, W2, w);
             if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
             const int r[3] = {sR[0], sR[1], sR[2]};
-            reconstruct(core, r, U, d, B, W1, W2, w.gw.tile);   // Density() sums the rounded tensor (particle_data.cpp:99)
+            reconstruct(core, r, U, d, B, W1, W2, w.gw.tile, w.prof);   // Density() sums the rounded tensor (particle_data.cpp:99)
         }
         double acc = 0.0;
         for (int e = threadIdx.x; e < N; e += blockDim.x) acc += B[e];
@@ -693,6 +728,10 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
         }
         __syncthreads();
     }
+    if (w.prof) {
+        sProf[7] = clock64() - tKernel;
+        for (int i = 0; i < 8; i++) P.prof[i] = sProf[i];
+    }
 }
 
 }  // namespace
@@ -705,6 +744,7 @@ void tucker_destroy(TuckerState* ts)
     cudaFree(ts->ranks[0]);
     cudaFree(ts->ranks[1]);
     cudaFree(ts->vnabs);
+    cudaFree(ts->vnabsRanks);
     cudaFree(ts->scratch);
     delete ts;
 }
@@ -728,6 +768,8 @@ void fill_params(vt_ctx* ctx, Species& sp, TuckerState& ts, TuckerParams& P)
     P.rec = sp.rec;
     P.E = ctx->E;
     P.vnabs = ts.vnabs;
+    P.vnabsRanks = ts.vnabsRanks;
+    P.vslot = ts.vslot;
     P.src = sp.src;
     P.density = sp.density;
     P.wall = sp.wall;
@@ -861,7 +903,9 @@ int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
             VT_CUDA(cudaMalloc(&ts->ranks[b], nA * 3 * sizeof(int)));
             VT_CUDA(cudaMemset(ts->ranks[b], 0, nA * 3 * sizeof(int)));
         }
-        VT_CUDA(cudaMalloc(&ts->vnabs, nA * 4 * sp.N * sizeof(double)));
+        ts->vslot = 216 + 6 * (size_t)(sp.n[0] + sp.n[1] + sp.n[2]);
+        VT_CUDA(cudaMalloc(&ts->vnabs, nA * 4 * ts->vslot * sizeof(double)));
+        VT_CUDA(cudaMalloc(&ts->vnabsRanks, nA * 12 * sizeof(int)));
         ts->scratchCTAs = 2 * ctx->prop.multiProcessorCount;
         const size_t per = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
         VT_CUDA(cudaMalloc(&ts->scratch, (size_t)ts->scratchCTAs * per * sizeof(double)));
@@ -972,9 +1016,27 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
         P.dt = dt;
         for (int k = 0; k < 3; k++) P.ext[k] = ext ? ext[k] : 0.0;
         P.wallScale = sp.charge * dt * sp.cellVolume;
+        // VT_TUCKER_PROFILE=1: per-phase clock cycles of thread 0 of CTA 0, printed to stderr
+        static const bool profile = getenv("VT_TUCKER_PROFILE") != nullptr;
+        long long* profDev = nullptr;
+        if (profile) {
+            VT_CUDA(cudaMalloc(&profDev, 8 * sizeof(long long)));
+            VT_CUDA(cudaMemsetAsync(profDev, 0, 8 * sizeof(long long), ctx->stream));
+            P.prof = profDev;
+        }
         VT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
         launch(ctx, ts, P);
         VT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        if (profile) {
+            long long h[8];
+            VT_CUDA(cudaStreamSynchronize(ctx->stream));
+            VT_CUDA(cudaMemcpy(h, profDev, sizeof(h), cudaMemcpyDeviceToHost));
+            cudaFree(profDev);
+            fprintf(stderr,
+                    "[vt_step_tucker] cycles of CTA 0: gram %lld  eig %lld  select %lld  project %lld  reconstruct %lld  "
+                    "flux %lld  derivative %lld  total %lld\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        }
         ts.cur ^= 1;
         ts.denseValid = false;
         sp.densityValid = true;
