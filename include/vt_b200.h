@@ -181,6 +181,13 @@ int vt_tucker_density(vt_ctx* ctx, int species, double* density);
 /* Solver<Tucker>::_UpdatePDF for one species (src/solver.cpp:141-212): flux per face, rounding
  * after each face, acceleration term, rounding, Euler update, rounding */
 int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3]);
+/* multi-GPU Tucker species (after vt_halo_export/attach/set_push of the same species and after the
+ * last vt_tucker_enable): 128-byte handle of the compressed state to hand to the peers, and the
+ * peers' handles in the order of vt_halo_attach.  vt_step_tucker then also stores every boundary
+ * tet's new core, factors and ranks into the peers' ghost rows (fixed-capacity slots), and
+ * vt_halo_push_current / vt_halo_barrier serve the species as they do for the full format. */
+int vt_tucker_halo_export(vt_ctx* ctx, int species, void* handle);
+int vt_tucker_halo_attach(vt_ctx* ctx, int species, int nPeers, const void* peerHandles);
 
 #ifdef __cplusplus
 }

@@ -136,6 +136,45 @@ def test_generic_entry_points_on_tucker_species(oracle_mod):
     ctx.close()
 
 
+@pytest.mark.parametrize("n,cap", [((32, 24, 20), 0), ((48, 40, 36), 8), ((20, 64, 18), 8)])
+def test_large_grids_against_dense_statement(n, cap):
+    """Velocity grids above 16 nodes per axis take the 256-thread kernel (tiled Gram matrices with
+    and without register prefetch, C5 shape 48^3 at rank 8).  The oracle's Tucker algebra is too
+    slow there, so the check is against the numpy dense + SVD statement of the same update
+    (tests/tucker_dense_ref.py, itself pinned to the oracle in test_tucker_cpu.py)."""
+    import vlasovtucker_b200 as vtb
+    from vlasovtucker_b200 import synthetic
+    mt = synthetic.periodic_kuhn_tables(2, 1, 1, (1.0, 0.5, 0.5), brick=(1, 1, 1))
+    vmin, vmax = [-3.0, -2.5, -2.0], [3.0, 2.5, 2.0]
+    eps, dt = 1e-6, 2e-3
+    _, V = vgrid(n, vmin, vmax)
+    rng = np.random.default_rng(8)
+    f = np.zeros((mt.nTets, n[0] * n[1] * n[2]))
+    for t in range(mt.nTets):      # a few drifting anisotropic Maxwellians per tet: rank > 1
+        for _ in range(3):
+            c, s = rng.uniform(-0.8, 0.8, 3), rng.uniform(0.5, 1.0, 3)
+            f[t] += rng.uniform(0.5, 1.5) * np.exp(-0.5 * sum(((V[k] - c[k]) / s[k]) ** 2 for k in range(3)))
+    E = rng.standard_normal((mt.nTets, 3))
+    ctx = vtb.Context(0)
+    ctx.mesh_upload(mt)
+    g = ctx.species_create(n, vmin, vmax, 1.0, 1.0)
+    bc = np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8)
+    ctx.set_face_bc(g, bc)
+    ctx.tucker_enable(g, eps, cap)
+    ctx.tucker_set_pdf(g, f)
+    ctx.field_set(E)
+    ctx.step_tucker(g, dt)
+    rmax = cap if cap else max(n)
+    if cap:   # the initial tensors are stored with rank <= cap (DESIGN.md §4)
+        f = np.stack([tdr.truncate(row.reshape(n, order="F"), 0.0, cap)[0].ravel(order="F") for row in f])
+    gd, ranks = tdr.step_dense(f, mt.nbr, mt.area, mt.volume, mt.normal, bc, n, vmin, vmax, 1.0, E, dt, eps, rmax)
+    fg = ctx.tucker_get_pdf(g, f.shape[1])
+    assert rel_l2(fg, gd) <= eps + 1e-10
+    assert np.abs(ctx.tucker_ranks(g) - ranks).max() <= 1
+    assert ctx.tucker_ranks(g).max() > 1
+    ctx.close()
+
+
 def test_max_rank_cap(oracle_mod):
     """ParticleData::SetMaxRank (C5: 48^3 at r = 8): ranks never exceed the cap and the capped
     rounding matches the oracle's."""

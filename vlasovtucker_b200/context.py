@@ -280,6 +280,17 @@ class Context:
         capi.check(self.lib.vt_tucker_density(self.h, sp, capi.dp(d)))
         return d
 
+    TUCKER_HALO_HANDLE_BYTES = 128
+
+    def tucker_halo_export(self, sp):
+        buf = np.zeros(self.TUCKER_HALO_HANDLE_BYTES, np.uint8)
+        capi.check(self.lib.vt_tucker_halo_export(self.h, sp, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    def tucker_halo_attach(self, sp, peer_handles):
+        h = np.ascontiguousarray(peer_handles, np.uint8).reshape(-1, self.TUCKER_HALO_HANDLE_BYTES)
+        capi.check(self.lib.vt_tucker_halo_attach(self.h, sp, len(h), h.ctypes.data_as(C.c_void_p)))
+
     def step_tucker(self, sp, dt, ext=(0.0, 0.0, 0.0)):
         ext = capi.f64(ext)
         capi.check(self.lib.vt_step_tucker(self.h, sp, float(dt), capi.dp(ext)))

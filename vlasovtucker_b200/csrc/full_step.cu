@@ -437,13 +437,15 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
         kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(p);
         VT_CUDA(cudaEventRecord(e1, ctx->stream));
     };
-    // variant bit 3: force the register-staged kernel even where the TMA pipeline applies
-    // bit 3: the persistent cp.async pipeline; bit 4: the persistent bulk-copy (TMA) producer.
-    // Both are measured slower than the register-staged kernel on B200 (profiles/round1_notes.md)
-    // and stay opt-in; they fall through to the register-staged kernel where they do not apply.
+    // bit 4: the persistent bulk-copy (cp.async.bulk) producer/consumer pipeline — it counts its own
+    // launches (one, or two when boundary and interior tets are launched separately); bit 3: the
+    // persistent cp.async pipeline (opt-in).  Both fall through to the register-staged kernel where
+    // they do not apply.
     bool useTma = false;
-    if (ctx->variant & 16) useTma = launch_full_step_tma(ctx, sp, p, upwind, e0, e1);
-    else if (ctx->variant & 8) useTma = launch_full_step_async(ctx, sp, p, upwind, e0, e1);
+    if (ctx->variant & 16) {
+        useTma = launch_full_step_tma(ctx, sp, p, upwind, e0, e1);
+        if (useTma) ctx->launches--;   // compensates the increment below
+    } else if (ctx->variant & 8) useTma = launch_full_step_async(ctx, sp, p, upwind, e0, e1);
     // variant bit 2: ask the compiler for 3 resident CTAs per SM (<= 85 registers) instead of 2
     const bool dense = (ctx->variant & 4) != 0;
     if (useTma) {

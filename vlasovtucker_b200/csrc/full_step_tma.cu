@@ -88,16 +88,20 @@ struct ItemHdr {
     double pad;
 };
 
-__device__ __forceinline__ bool decode_item(const StepParams& p, long long w, long long total, ItemHdr& it)
+// Work item w of a launch over nTets tets (all owned tets, or the sub-list tetList of them):
+// brick-major, then chunk, then tet.
+__device__ __forceinline__ bool decode_item(const StepParams& p, const int* __restrict__ tetList, int nTets, long long w,
+                                            long long total, ItemHdr& it)
 {
     if (w >= total) return false;
     const int perBrick = p.brickTets * p.nChunks;
     const int brick = (int)(w / perBrick);
     const int base = brick * p.brickTets;
-    const int nb = min(p.brickTets, p.nOwned - base);
+    const int nb = min(p.brickTets, nTets - base);
     const int r = (int)(w - (long long)brick * perBrick);
     it.chunk = r / nb;
-    it.tet = base + (r - it.chunk * nb);
+    const int pos = base + (r - it.chunk * nb);
+    it.tet = tetList ? tetList[pos] : pos;
     it.pl0 = it.chunk * p.chunkPlanes;
     it.npl = min(p.chunkPlanes, p.n2 - it.pl0);
     return true;
@@ -110,6 +114,8 @@ struct BulkParams {
     int PV;           // double2 per plane
     unsigned long long* queue;
     long long total;
+    const int* tetList;   // nullptr: all owned tets in device order
+    int nTets;
 };
 
 struct Smem {
@@ -149,7 +155,7 @@ __device__ void producer_loop(const BulkParams& P, const Smem& sm)
     auto post_item = [&](long long w) {   // header + tet record of the item into slot cPost
         mbar_wait(sm.itemEmpty + cPost.slot, cPost.phase ^ 1u);
         ItemHdr h;
-        if (decode_item(p, w, P.total, h)) {
+        if (decode_item(p, P.tetList, P.nTets, w, P.total, h)) {
             sm.hdr[cPost.slot].tet = h.tet;
             sm.hdr[cPost.slot].chunk = h.chunk;
             sm.hdr[cPost.slot].pl0 = h.pl0;
@@ -293,7 +299,9 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const double v0 = __dadd_rn(p.vmin[0], __dmul_rn((double)(col[kk].i0 + u), p.step[0]));
-                cxy[kk][f][u] = pre * (rec.nrm[f][0] * v0 + rec.nrm[f][1] * v1);
+                // explicit roundings here and below: every template instance of this function has to
+                // produce the same bits (a partitioned run mixes them, and must equal the single-GPU run)
+                cxy[kk][f][u] = __dmul_rn(pre, __fma_rn(rec.nrm[f][0], v0, __dmul_rn(rec.nrm[f][1], v1)));
             }
         }
     }
@@ -351,7 +359,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
 
         double tzf[4];
 #pragma unroll
-        for (int f = 0; f < 4; f++) tzf[f] = cz[f] * v2;
+        for (int f = 0; f < 4; f++) tzf[f] = __dmul_rn(cz[f], v2);
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
             if (!col[kk].on) continue;
@@ -381,14 +389,14 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
                 double rhs = 0.0;
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
-                    const double vn = cxy[kk][f][u] + tzf[f];
+                    const double vn = __dadd_rn(cxy[kk][f][u], tzf[f]);
                     const double fau = u == 0 ? fa[f].x : fa[f].y;
                     if (!GENERIC || pairF[f]) {
                         if (UPWIND) {
                             rhs = fma(-vn, vn > 0.0 ? fv : fau, rhs);
                         } else {
-                            const double s = fau + fv, d = fau - fv;
-                            rhs = fma(-hc[f], fma(vn, s, -(fabs(vn) * d)), rhs);
+                            const double s = __dadd_rn(fau, fv), d = __dsub_rn(fau, fv);
+                            rhs = __fma_rn(-hc[f], __fma_rn(vn, s, -__dmul_rn(fabs(vn), d)), rhs);
                         }
                     } else if (absF[f]) {
                         const double flux = 0.5 * (vn * fv + fabs(vn) * fv);
@@ -398,11 +406,11 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
                         rhs = fma(-hc[f], vn * fv, rhs);
                     }
                 }
-                rhs = fma(-g[0], xp[u] - xm[u], rhs);
-                rhs = fma(-g[1], y1p[u] - y1m[u], rhs);
-                rhs = fma(-g[2], z2p[u] - z2m[u], rhs);
+                rhs = __fma_rn(-g[0], __dsub_rn(xp[u], xm[u]), rhs);
+                rhs = __fma_rn(-g[1], __dsub_rn(y1p[u], y1m[u]), rhs);
+                rhs = __fma_rn(-g[2], __dsub_rn(z2p[u], z2m[u]), rhs);
                 out[u] = fma(p.dt, rhs, fv);
-                accDens += out[u];
+                accDens = __dadd_rn(accDens, out[u]);
             }
             const double2 o = make_double2(out[0], out[1]);
             *reinterpret_cast<double2*>(outp[kk]) = o;
@@ -440,15 +448,6 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
             if (lane == 0) atomicAdd(p.wall + rec.wallSlot[f], p.wallScale * rec.area[f] * wv);
         }
     }
-}
-
-// Boundary / halo-push tets are a small minority of a partition: keeping their code out of line
-// leaves the all-interior path with the registers it has in the ALLFAST kernel.
-template <int KPT, bool UPWIND, int NCW>
-__device__ __noinline__ void item_compute_generic(const BulkParams& P, const ConsRings& R, const ItemHdr& cur, const TetRec& rec,
-                                                  uint32_t& cOwn, uint32_t& cNbr, const Column (&col)[KPT])
-{
-    item_compute<KPT, UPWIND, true, NCW>(P, R, cur, rec, cOwn, cNbr, col);
 }
 
 template <int KPT, bool UPWIND, int NCW, bool ALLFAST>
@@ -534,7 +533,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
             const bool fast = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]) &&
                               rec.pushPeer[0] < 0;
             if (fast) item_compute<KPT, UPWIND, false, NCW>(P, R, cur, rec, cOwn, cNbr, col);
-            else item_compute_generic<KPT, UPWIND, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+            else item_compute<KPT, UPWIND, true, NCW>(P, R, cur, rec, cOwn, cNbr, col);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.itemEmpty + cItem.slot);
@@ -543,14 +542,15 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
 }
 
 template <int KPT, int NCW>
-void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, int grid, size_t smem, cudaEvent_t e0, cudaEvent_t e1)
+void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, size_t smem)
 {
+    if (P.total == 0) return;
+    const int grid = (int)std::min<long long>(P.total, ctx->prop.multiProcessorCount);
     auto launch = [&](auto kern) {
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         VT_CUDA(cudaMemsetAsync(ctx->workCounter, 0, sizeof(unsigned long long), ctx->stream));
-        VT_CUDA(cudaEventRecord(e0, ctx->stream));
         kern<<<grid, NCW * 32 + 32, smem, ctx->stream>>>(P);
-        VT_CUDA(cudaEventRecord(e1, ctx->stream));
+        ctx->launches++;
     };
     if (allFast) upwind ? launch(k_full_step_bulk<KPT, true, NCW, true>) : launch(k_full_step_bulk<KPT, false, NCW, true>);
     else upwind ? launch(k_full_step_bulk<KPT, true, NCW, false>) : launch(k_full_step_bulk<KPT, false, NCW, false>);
@@ -584,14 +584,27 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     const size_t smem = (size_t)OD * PB + (size_t)S * 4 * PB + fixed;
 
     if (sp.fastOnly < 0) {
-        // every face paired with a neighbour row (or a source row) and no halo push: the kernel
-        // without the boundary-condition branches applies
-        sp.fastOnly = 1;
-        for (const TetRec& r : sp.recHost) {
+        // Tets whose four faces are all paired with a neighbour (or source) row and that push no halo
+        // copy take the kernel without the boundary-condition branches.  When both kinds exist they
+        // are launched separately — boundary/halo tets first, so that their peer stores overlap the
+        // interior work — each over its own list (device order kept, so bricks still mean locality).
+        std::vector<int32_t> gen, fast;
+        for (int t = 0; t < ctx->nOwned; t++) {
+            const TetRec& r = sp.recHost[t];
+            bool g = r.pushPeer[0] >= 0;
             for (int f = 0; f < 4; f++)
-                if (!(r.bc[f] == VT_PBC_NONBOUNDARY || r.bc[f] == VT_PBC_PERIODIC || r.bc[f] == VT_PBC_SOURCE)) sp.fastOnly = 0;
-            if (r.pushPeer[0] >= 0) sp.fastOnly = 0;
-            if (!sp.fastOnly) break;
+                if (!(r.bc[f] == VT_PBC_NONBOUNDARY || r.bc[f] == VT_PBC_PERIODIC || r.bc[f] == VT_PBC_SOURCE)) g = true;
+            (g ? gen : fast).push_back(t);
+        }
+        sp.fastOnly = gen.empty() ? 1 : 0;
+        if (sp.tetLists) VT_CUDA(cudaFree(sp.tetLists));
+        sp.tetLists = nullptr;
+        sp.nGeneric = (int)gen.size();
+        sp.nFast = (int)fast.size();
+        if (!gen.empty()) {
+            gen.insert(gen.end(), fast.begin(), fast.end());
+            VT_CUDA(cudaMalloc(&sp.tetLists, gen.size() * sizeof(int32_t)));
+            VT_CUDA(cudaMemcpy(sp.tetLists, gen.data(), gen.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         }
     }
     if (!ctx->workCounter) VT_CUDA(cudaMalloc(&ctx->workCounter, sizeof(unsigned long long)));
@@ -602,15 +615,25 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     P.planeElems = PE;
     P.PV = PV;
     P.queue = ctx->workCounter;
-    P.total = (long long)ctx->nOwned * p.nChunks;
-    const int grid = (int)std::min<long long>(P.total, ctx->prop.multiProcessorCount);
-    const bool allFast = sp.fastOnly == 1;
 
-    if (wide) launch_cfg<2, 8>(ctx, P, upwind, allFast, grid, smem, e0, e1);
-    else if (kpt == 1) launch_cfg<1, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
-    else if (kpt == 2) launch_cfg<2, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
-    else if (kpt == 3) launch_cfg<3, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
-    else launch_cfg<4, 16>(ctx, P, upwind, allFast, grid, smem, e0, e1);
+    auto run = [&](const int* list, int nTets, bool allFast) {
+        P.tetList = list;
+        P.nTets = nTets;
+        P.total = (long long)nTets * p.nChunks;
+        if (wide) launch_cfg<2, 8>(ctx, P, upwind, allFast, smem);
+        else if (kpt == 1) launch_cfg<1, 16>(ctx, P, upwind, allFast, smem);
+        else if (kpt == 2) launch_cfg<2, 16>(ctx, P, upwind, allFast, smem);
+        else if (kpt == 3) launch_cfg<3, 16>(ctx, P, upwind, allFast, smem);
+        else launch_cfg<4, 16>(ctx, P, upwind, allFast, smem);
+    };
+    VT_CUDA(cudaEventRecord(e0, ctx->stream));
+    if (sp.fastOnly == 1) {
+        run(nullptr, ctx->nOwned, true);
+    } else {
+        run(sp.tetLists, sp.nGeneric, false);
+        run(sp.tetLists + sp.nGeneric, sp.nFast, true);
+    }
+    VT_CUDA(cudaEventRecord(e1, ctx->stream));
     VT_CUDA(cudaGetLastError());
     p.densSplit = ncw;
     return true;

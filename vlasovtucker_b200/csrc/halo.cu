@@ -142,6 +142,10 @@ int vt_halo_push_current(vt_ctx* ctx, int species)
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
+        if (sp.tucker) {
+            vt::tucker_push_current(ctx, sp);
+            return;
+        }
         if (ctx->nOwned == 0 || sp.nPeers == 0) return;
         double* base[vt::kMaxPeers];
         for (int i = 0; i < vt::kMaxPeers; i++) base[i] = i < sp.nPeers ? sp.peerF[i][sp.cur] : nullptr;

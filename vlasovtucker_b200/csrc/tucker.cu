@@ -32,8 +32,14 @@ namespace vt {
 struct TuckerState {
     int rcap[3];                 // stored rank capacity per mode = min(maxRank, n)
     size_t coreCap, slot;        // doubles per tet: core, whole slot (core + 3 factors)
+    void* block = nullptr;       // one allocation (one CUDA-IPC handle): buf[0] | buf[1] | ranks[0] | ranks[1]
+    size_t rows = 0;             // owned + ghost rows
     double* buf[2] = {nullptr, nullptr};   // compressed state, ping-pong
     int* ranks[2] = {nullptr, nullptr};    // 3 per tet
+    // multi-GPU: the peers' blocks, for the ghost copies of boundary tets
+    double* peerBuf[kMaxPeers][2] = {};
+    int* peerRanks[kMaxPeers][2] = {};
+    int nPeers = 0;
     double* vnabs = nullptr;     // |v.n| per face as rank-<=6 Tucker tensors (solver.cpp:282): 4 slots per owned tet
     int* vnabsRanks = nullptr;   // 3 per (tet, face)
     size_t vslot = 0;            // doubles per slot: 6^3 core + 6 (n0 + n1 + n2)
@@ -48,7 +54,8 @@ struct TuckerState {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;        // CTA size for velocity grids above 16 nodes per axis
+constexpr int kThreadsSmall = 128;   // ... and up to 16: more tets in flight per SM hide the eigen-solver's latency
 constexpr int kMaxN = 64;
 
 struct Dims {
@@ -111,7 +118,8 @@ __device__ void mode_apply(const double* __restrict__ src, double* __restrict__ 
 // tiles.  Each thread owns a fixed set of (i <= j) entries (pair table in shared memory) and keeps
 // them in registers across tiles; G is written symmetric with leading dimension ld = n | 1 (odd, so
 // that both row and column walks are bank-conflict free in the eigen-solver).
-constexpr int kMaxPairsPerThread = (kMaxN * (kMaxN + 1) / 2 + kThreads - 1) / kThreads;   // 9
+// pairs per thread: 64*65/2 over 256 threads, or 16*17/2 over 128
+template <int T> struct PairsPerThread { static constexpr int value = T == kThreads ? (kMaxN * (kMaxN + 1) / 2 + T - 1) / T : (16 * 17 / 2 + T - 1) / T; };
 
 struct GramWork {
     double* tile;              // tileCap = (nmax | 1) * nmax doubles
@@ -132,16 +140,19 @@ __device__ void build_pairs(unsigned short* pairs, int nmax)
     __syncthreads();
 }
 
+constexpr int kPrefetch = 4;   // doubles per thread held for the next Gram tile
+
+template <int T>
 __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode, double* __restrict__ G, const GramWork& gw)
 {
     const int n = d[mode];
     const int np = pair_count(n);
-    double acc[kMaxPairsPerThread];
-    int pi[kMaxPairsPerThread], pj[kMaxPairsPerThread];
+    double acc[PairsPerThread<T>::value];
+    int pi[PairsPerThread<T>::value], pj[PairsPerThread<T>::value];
 #pragma unroll
-    for (int k = 0; k < kMaxPairsPerThread; k++) {
+    for (int k = 0; k < PairsPerThread<T>::value; k++) {
         acc[k] = 0.0;
-        const int q = threadIdx.x + k * kThreads;
+        const int q = threadIdx.x + k * T;
         const unsigned short pr = q < np ? gw.pairs[q] : 0;
         pi[k] = pr & 255;
         pj[k] = pr >> 8;
@@ -150,13 +161,38 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
     if (mode == 0 || mode == 1) {
         // slabs A = X(:, :, i2), n0 x n1; mode 0: G += A A^T, mode 1: G += A^T A
         const int ld = mode == 0 ? n0 : (n0 | 1);
+        // the next slab is fetched into registers while the current one is consumed from shared memory
+        const bool pf = M <= kPrefetch * T;
+        double pre[kPrefetch];
+        if (pf) {
+#pragma unroll
+            for (int q = 0; q < kPrefetch; q++) {
+                const int e = threadIdx.x + q * T;
+                pre[q] = e < M ? X[e] : 0.0;
+            }
+        }
         for (int i2 = 0; i2 < n2; i2++) {
             const double* slab = X + (size_t)i2 * M;
-            for (int e = threadIdx.x; e < M; e += blockDim.x) gw.tile[(e % n0) + ld * (e / n0)] = slab[e];
-            __syncthreads();
+            if (pf) {
 #pragma unroll
-            for (int k = 0; k < kMaxPairsPerThread; k++) {
-                if (threadIdx.x + k * kThreads >= np) break;
+                for (int q = 0; q < kPrefetch; q++) {
+                    const int e = threadIdx.x + q * T;
+                    if (e < M) gw.tile[(e % n0) + ld * (e / n0)] = pre[q];
+                }
+            } else {
+                for (int e = threadIdx.x; e < M; e += blockDim.x) gw.tile[(e % n0) + ld * (e / n0)] = slab[e];
+            }
+            __syncthreads();
+            if (pf && i2 + 1 < n2) {
+#pragma unroll
+                for (int q = 0; q < kPrefetch; q++) {
+                    const int e = threadIdx.x + q * T;
+                    pre[q] = e < M ? slab[M + e] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PairsPerThread<T>::value; k++) {
+                if (threadIdx.x + k * T >= np) break;
                 double s = acc[k];
                 if (mode == 0) {
                     const double* a = gw.tile + pi[k];
@@ -174,18 +210,46 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
     } else {
         // X as an M x n2 matrix B (column a = plane a); G = B^T B over row chunks of Tr rows
         const int ldmax = gw.tileCap / n2;                       // the chunk (ld x n2) has to fit the tile
-        const int rows = min(M, (ldmax & 1) ? ldmax : ldmax - 1);
+        const int rowsFit = min(M, (ldmax & 1) ? ldmax : ldmax - 1);
+        const int rowsPf = kPrefetch * T / n2;                    // a chunk the register prefetch can hold
+        const bool pf = rowsPf >= 8;
+        const int rows = pf ? min(rowsFit, rowsPf) : rowsFit;
         const int ld = rows | 1;
+        double pre[kPrefetch];
+        if (pf) {
+            const int nr = min(rows, M);
+#pragma unroll
+            for (int q = 0; q < kPrefetch; q++) {
+                const int e = threadIdx.x + q * T;
+                pre[q] = e < nr * n2 ? X[(size_t)(e % nr) + (size_t)M * (e / nr)] : 0.0;
+            }
+        }
         for (int r0 = 0; r0 < M; r0 += rows) {
             const int nr = min(rows, M - r0);
-            for (int e = threadIdx.x; e < nr * n2; e += blockDim.x) {
-                const int r = e % nr, a = e / nr;
-                gw.tile[r + ld * a] = X[(size_t)r0 + r + (size_t)M * a];
+            if (pf) {
+#pragma unroll
+                for (int q = 0; q < kPrefetch; q++) {
+                    const int e = threadIdx.x + q * T;
+                    if (e < nr * n2) gw.tile[(e % nr) + ld * (e / nr)] = pre[q];
+                }
+            } else {
+                for (int e = threadIdx.x; e < nr * n2; e += blockDim.x) {
+                    const int r = e % nr, a = e / nr;
+                    gw.tile[r + ld * a] = X[(size_t)r0 + r + (size_t)M * a];
+                }
             }
             __syncthreads();
+            if (pf && r0 + rows < M) {
+                const int rn = r0 + rows, nrn = min(rows, M - rn);
 #pragma unroll
-            for (int k = 0; k < kMaxPairsPerThread; k++) {
-                if (threadIdx.x + k * kThreads >= np) break;
+                for (int q = 0; q < kPrefetch; q++) {
+                    const int e = threadIdx.x + q * T;
+                    pre[q] = e < nrn * n2 ? X[(size_t)rn + (e % nrn) + (size_t)M * (e / nrn)] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PairsPerThread<T>::value; k++) {
+                if (threadIdx.x + k * T >= np) break;
                 const double* a = gw.tile + ld * pi[k];
                 const double* b = gw.tile + ld * pj[k];
                 double s = acc[k];
@@ -197,8 +261,8 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
     }
     const int ldg = n | 1;
 #pragma unroll
-    for (int k = 0; k < kMaxPairsPerThread; k++) {
-        if (threadIdx.x + k * kThreads >= np) break;
+    for (int k = 0; k < PairsPerThread<T>::value; k++) {
+        if (threadIdx.x + k * T >= np) break;
         G[pi[k] + ldg * pj[k]] = acc[k];
         G[pj[k] + ldg * pi[k]] = acc[k];
     }
@@ -238,7 +302,7 @@ __device__ void eig_sym_warp(double* V, int n, int ld, double* dv, double* ev)
         } else {
             part = 0.0;
             for (int k = lane; k < i; k += 32) {
-                const double x = dv[k] / scale;
+                const double x = dv[k] / scale;   // scale may be subnormal: no reciprocal here
                 dv[k] = x;
                 part += x * x;
             }
@@ -264,8 +328,9 @@ __device__ void eig_sym_warp(double* V, int n, int ld, double* dv, double* ev)
             __syncwarp();
             for (int j = lane; j < i; j += 32) VV(j, i) = dv[j];
             part = 0.0;
+            const double hinv = 1.0 / h;
             for (int j = lane; j < i; j += 32) {
-                const double x = ev[j] / h;
+                const double x = ev[j] * hinv;
                 ev[j] = x;
                 part += x * dv[j];
             }
@@ -297,7 +362,8 @@ __device__ void eig_sym_warp(double* V, int n, int ld, double* dv, double* ev)
         __syncwarp();
         const double h = dv[i + 1];
         if (h != 0.0) {
-            for (int k = lane; k <= i; k += 32) dv[k] = VV(k, i + 1) / h;
+            const double hinv = 1.0 / h;
+            for (int k = lane; k <= i; k += 32) dv[k] = VV(k, i + 1) * hinv;
             __syncwarp();
             for (int j = lane; j <= i; j += 32) {
                 double g = 0.0;
@@ -344,7 +410,7 @@ __device__ void eig_sym_warp(double* V, int n, int ld, double* dv, double* ev)
                 iter++;
                 double g = dv[l];
                 double p = (dv[l + 1] - g) / (2.0 * ev[l]);
-                double r = hypot(p, 1.0);
+                double r = sqrt(fma(p, p, 1.0));
                 if (p < 0) r = -r;
                 const double el = ev[l];
                 const double dl = el / (p + r), dl1 = el * (p + r);
@@ -367,9 +433,26 @@ __device__ void eig_sym_warp(double* V, int n, int ld, double* dv, double* ev)
                     const double ei = ev[i], di = dv[i];
                     g = c * ei;
                     h = c * p;
-                    r = hypot(p, ei);
-                    s = ei / r;
-                    c = p / r;
+                    // r = hypot(p, e_i), s = e_i / r, c = p / r.  Scaling by a power of two (exact) keeps the
+                    // squares of the subnormal noise entries of a rank-deficient Gram matrix from
+                    // underflowing; one reciprocal square root replaces the divisions.
+                    {
+                        const double mx = fmax(fabs(p), fabs(ei));
+                        if (mx == 0.0) {
+                            r = 0.0;
+                            s = 0.0;
+                            c = 1.0;
+                        } else {
+                            int ex;
+                            (void)frexp(mx, &ex);
+                            const double a = scalbn(p, -ex), b = scalbn(ei, -ex);
+                            const double q2 = fma(a, a, b * b);      // in [0.25, 2)
+                            const double qinv = rsqrt(q2);
+                            r = scalbn(q2 * qinv, ex);
+                            s = b * qinv;
+                            c = a * qinv;
+                        }
+                    }
                     p = c * di - s * g;
                     __syncwarp();
                     if (lane == 0) {
@@ -416,14 +499,30 @@ struct TruncWork {
 // Truncated HOSVD of the dense tensor X (dims d).  Writes the factors to Uout[k] (leading dimension
 // d[k], rcap[k] columns available), the core to coreOut (r0 x r1 x r2 packed), the ranks to rsel.
 // W1/W2 are dense work buffers (>= N doubles each).
+template <int T>
 __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int rmax, const int rcap[3], double* const Uout[3],
                                double* coreOut, double* W1, double* W2, const TruncWork& w)
 {
     long long t0 = clock64();
-    for (int k = 0; k < 3; k++) gram_mode(X, d, k, w.G[k], w.gw);
+    for (int k = 0; k < 3; k++) gram_mode<T>(X, d, k, w.G[k], w.gw);
     long long t1 = clock64();
     if (w.prof) w.prof[0] += t1 - t0;
     const int warp = threadIdx.x >> 5;
+    if (warp < 3) {
+        // unit trace: the rank rule only uses ratios of eigenvalues, and the QL iteration can then
+        // use plain square roots
+        double* G = w.G[warp];
+        const int n = d[warp], ld = n | 1, lane = threadIdx.x & 31;
+        double tr = 0.0;
+        for (int i = lane; i < n; i += 32) tr += G[i + ld * i];
+        tr = wsum(tr);
+        if (tr > 0.0) {
+            const double inv = 1.0 / tr;
+            for (int j = 0; j < n; j++)
+                for (int i = lane; i < n; i += 32) G[i + ld * j] *= inv;
+        }
+        __syncwarp();
+    }
     if (warp < 3) eig_sym_warp(w.G[warp], d[warp], d[warp] | 1, w.dv + warp * kMaxN, w.ev + warp * kMaxN);
     __syncthreads();
     t0 = clock64();
@@ -523,6 +622,8 @@ struct TuckerParams {
     int mode;                // 0 step, 1 compress dense input, 2 reconstruct, 3 |v.n| tables
     double epsAbs;           // mode 3: compression error for |v.n| (rank cap 6)
     long long* prof;         // optional: 8 phase timers in clock cycles (VT_TUCKER_PROFILE)
+    double* peerOut[kMaxPeers];   // multi-GPU: peers' state buffers receiving the ghost copies
+    int* peerRout[kMaxPeers];
 };
 
 __device__ void slot_ptrs(double* base, const TuckerParams& P, double*& core, double* U[3])
@@ -533,7 +634,8 @@ __device__ void slot_ptrs(double* base, const TuckerParams& P, double*& core, do
     U[2] = U[1] + (size_t)P.n[1] * P.rcap[1];
 }
 
-__global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
+template <int T>
+__global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const TuckerParams P)
 {
     extern __shared__ double sDyn[];   // 3 Gram/eigenvector matrices + one staging tile, (nmax|1)*nmax doubles each
     const int nmaxS = max(P.n[0], max(P.n[1], P.n[2]));
@@ -542,7 +644,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
     __shared__ int sOrder[3 * kMaxN];
     __shared__ unsigned short sPairs[kMaxN * (kMaxN + 1) / 2];
     __shared__ int sR[3];
-    __shared__ double sRed[kThreads / 32][5];
+    __shared__ double sRed[T / 32][5];
     __shared__ TetRec rec;
     TruncWork w;
     for (int k = 0; k < 3; k++) w.G[k] = sDyn + (size_t)k * matElems;
@@ -584,7 +686,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             slot_ptrs(P.out + (size_t)t * P.slot, P, core, U);
             for (int e = threadIdx.x; e < N; e += blockDim.x) A[e] = P.denseIn[(size_t)t * N + e];
             __syncthreads();
-            hosvd_truncate(A, d, 0.0, P.maxRank, P.rcap, U, core, W1, W2, w);
+            hosvd_truncate<T>(A, d, 0.0, P.maxRank, P.rcap, U, core, W1, W2, w);
             if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
             __syncthreads();
             continue;
@@ -596,6 +698,17 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             for (int i = threadIdx.x; i < (int)(sizeof(TetRec) / 4); i += blockDim.x) s[i] = g[i];
         }
         __syncthreads();
+        if (P.mode == 4) {   // initial ghost fill: copy the current slot of every pushing tet to its peers
+            for (int q = 0; q < 4; q++) {
+                if (rec.pushPeer[q] < 0) continue;
+                const double* src = P.in + (size_t)t * P.slot;
+                double* dst = P.peerOut[rec.pushPeer[q]] + (size_t)rec.pushRow[q] * P.slot;
+                for (size_t e = threadIdx.x; e < P.slot; e += blockDim.x) dst[e] = src[e];
+                if (threadIdx.x < 3) P.peerRout[rec.pushPeer[q]][3 * (size_t)rec.pushRow[q] + threadIdx.x] = P.rin[3 * t + threadIdx.x];
+            }
+            __syncthreads();
+            continue;
+        }
         if (P.mode == 3) {   // |v.n| per face, rounded to rank <= 6 (solver.cpp:276-282)
             for (int f = 0; f < 4; f++) {
                 for (int e = threadIdx.x; e < N; e += blockDim.x) {
@@ -609,7 +722,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
                 double* vs = P.vnabs + ((size_t)t * 4 + f) * P.vslot;
                 double* Uv[3] = {vs + 216, vs + 216 + 6 * d[0], vs + 216 + 6 * (d[0] + d[1])};
                 const int cap6[3] = {min(6, d[0]), min(6, d[1]), min(6, d[2])};
-                hosvd_truncate(A, d, P.epsAbs, 6, cap6, Uv, vs, W1, W2, w);
+                hosvd_truncate<T>(A, d, P.epsAbs, 6, cap6, Uv, vs, W1, W2, w);
                 if (threadIdx.x < 3) P.vnabsRanks[((size_t)t * 4 + f) * 3 + threadIdx.x] = sR[threadIdx.x];
                 __syncthreads();
             }
@@ -670,7 +783,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             __syncthreads();
             if (w.prof) w.prof[5] += clock64() - tFlux;
             // rhs.Compress(comprErr, maxRank)                                           solver.cpp:182
-            hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);
+            hosvd_truncate<T>(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);
             const int r[3] = {sR[0], sR[1], sR[2]};
             reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile, w.prof);
         }
@@ -694,7 +807,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
             for (int e = threadIdx.x; e < N; e += blockDim.x) RHS[e] = W1[e];
             __syncthreads();
             if (w.prof) w.prof[6] += clock64() - tDer;
-            hosvd_truncate(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);   // solver.cpp:199
+            hosvd_truncate<T>(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);   // solver.cpp:199
             const int r[3] = {sR[0], sR[1], sR[2]};
             reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile, w.prof);
         }
@@ -704,10 +817,18 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
         {
             double *core, *U[3];
             slot_ptrs(P.out + (size_t)t * P.slot, P, core, U);
-            hosvd_truncate(B, d, P.eps, P.maxRank, P.rcap, U, core, W1, W2, w);
+            hosvd_truncate<T>(B, d, P.eps, P.maxRank, P.rcap, U, core, W1, W2, w);
             if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
             const int r[3] = {sR[0], sR[1], sR[2]};
             reconstruct(core, r, U, d, B, W1, W2, w.gw.tile, w.prof);   // Density() sums the rounded tensor (particle_data.cpp:99)
+            // multi-GPU: the new slot of a boundary tet also goes into the ghost rows of the peers
+            for (int q = 0; q < 4; q++) {
+                if (rec.pushPeer[q] < 0) continue;
+                const double* src = P.out + (size_t)t * P.slot;
+                double* dst = P.peerOut[rec.pushPeer[q]] + (size_t)rec.pushRow[q] * P.slot;
+                for (size_t e = threadIdx.x; e < P.slot; e += blockDim.x) dst[e] = src[e];
+                if (threadIdx.x < 3) P.peerRout[rec.pushPeer[q]][3 * (size_t)rec.pushRow[q] + threadIdx.x] = r[threadIdx.x];
+            }
         }
         double acc = 0.0;
         for (int e = threadIdx.x; e < N; e += blockDim.x) acc += B[e];
@@ -720,7 +841,7 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
         __syncthreads();
         if (threadIdx.x == 0) {
             double tot[5] = {0, 0, 0, 0, 0};
-            for (int wv = 0; wv < kThreads / 32; wv++)
+            for (int wv = 0; wv < T / 32; wv++)
                 for (int q = 0; q < 5; q++) tot[q] += sRed[wv][q];
             P.density[t] = tot[0] * P.cellVolume;
             for (int f = 0; f < 4; f++)
@@ -736,13 +857,18 @@ __global__ void __launch_bounds__(kThreads) k_tucker(const TuckerParams P)
 
 }  // namespace
 
+static void tucker_block_pointers(void* block, size_t rows, size_t slot, double* buf[2], int* ranks[2])
+{
+    buf[0] = static_cast<double*>(block);
+    buf[1] = buf[0] + rows * slot;
+    ranks[0] = reinterpret_cast<int*>(buf[1] + rows * slot);
+    ranks[1] = ranks[0] + rows * 3;
+}
+
 void tucker_destroy(TuckerState* ts)
 {
     if (!ts) return;
-    cudaFree(ts->buf[0]);
-    cudaFree(ts->buf[1]);
-    cudaFree(ts->ranks[0]);
-    cudaFree(ts->ranks[1]);
+    cudaFree(ts->block);
     cudaFree(ts->vnabs);
     cudaFree(ts->vnabsRanks);
     cudaFree(ts->scratch);
@@ -787,9 +913,14 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     const int grid = std::min(ctx->nOwned, ts.scratchCTAs);
     const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
     const size_t smem = (3 * (size_t)(nmax | 1) + std::max(nmax | 1, (nmax + kQB - 1) / kQB * kQB)) * nmax * sizeof(double);
-    if (smem > 32 * 1024)
-        VT_CUDA(cudaFuncSetAttribute(k_tucker, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
-    k_tucker<<<grid, kThreads, smem, ctx->stream>>>(P);
+    if (nmax <= 16) {
+        k_tucker<kThreadsSmall><<<grid, kThreadsSmall, smem, ctx->stream>>>(P);
+    } else {
+        if (smem > 32 * 1024)
+            VT_CUDA(cudaFuncSetAttribute(k_tucker<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         4 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
+        k_tucker<kThreads><<<grid, kThreads, smem, ctx->stream>>>(P);
+    }
     ctx->launches++;
     VT_CUDA(cudaGetLastError());
 }
@@ -853,6 +984,25 @@ void tucker_from_dense(vt_ctx* ctx, Species& sp)
     ts.denseValid = ts.maxRank >= std::max({sp.n[0], sp.n[1], sp.n[2]});
 }
 
+// Initial ghost fill of a partitioned Tucker species (vt_halo_push_current dispatches here).
+void tucker_push_current(vt_ctx* ctx, Species& sp)
+{
+    TuckerState& ts = state_of(sp);
+    if (ctx->nOwned == 0 || sp.nPeers == 0) return;
+    if (ts.nPeers != sp.nPeers) throw std::runtime_error("partitioned Tucker species: vt_tucker_halo_attach has not been called");
+    TuckerParams P;
+    fill_params(ctx, sp, ts, P);
+    P.mode = 4;
+    P.in = ts.buf[ts.cur];
+    P.rin = ts.ranks[ts.cur];
+    for (int i = 0; i < kMaxPeers; i++) {
+        P.peerOut[i] = i < ts.nPeers ? ts.peerBuf[i][ts.cur] : nullptr;
+        P.peerRout[i] = i < ts.nPeers ? ts.peerRanks[i][ts.cur] : nullptr;
+    }
+    launch(ctx, ts, P);
+    VT_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
 namespace {
 
 void ensure_vnabs(vt_ctx* ctx, Species& sp, TuckerState& ts)
@@ -878,7 +1028,6 @@ int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
-        if (ctx->nGhost > 0) throw std::runtime_error("the Tucker path is single-GPU for now");
         for (int k = 0; k < 3; k++)
             if (sp.n[k] > kMaxN) throw std::runtime_error("Tucker path: velocity grid larger than 64 nodes per axis");
         if (sp.tucker) {
@@ -897,20 +1046,61 @@ int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
         ts->coreCap = (size_t)ts->rcap[0] * ts->rcap[1] * ts->rcap[2];
         ts->slot = ts->coreCap + (size_t)sp.n[0] * ts->rcap[0] + (size_t)sp.n[1] * ts->rcap[1] + (size_t)sp.n[2] * ts->rcap[2];
         const size_t nA = std::max(1, ctx->nOwned);
-        for (int b = 0; b < 2; b++) {
-            VT_CUDA(cudaMalloc(&ts->buf[b], nA * ts->slot * sizeof(double)));
-            VT_CUDA(cudaMemset(ts->buf[b], 0, nA * ts->slot * sizeof(double)));
-            VT_CUDA(cudaMalloc(&ts->ranks[b], nA * 3 * sizeof(int)));
-            VT_CUDA(cudaMemset(ts->ranks[b], 0, nA * 3 * sizeof(int)));
-        }
+        ts->rows = (size_t)std::max(1, ctx->nOwned + ctx->nGhost);
+        const size_t blockBytes = 2 * ts->rows * ts->slot * sizeof(double) + 2 * ts->rows * 3 * sizeof(int);
+        VT_CUDA(cudaMalloc(&ts->block, blockBytes));
+        VT_CUDA(cudaMemset(ts->block, 0, blockBytes));
+        tucker_block_pointers(ts->block, ts->rows, ts->slot, ts->buf, ts->ranks);
         ts->vslot = 216 + 6 * (size_t)(sp.n[0] + sp.n[1] + sp.n[2]);
         VT_CUDA(cudaMalloc(&ts->vnabs, nA * 4 * ts->vslot * sizeof(double)));
         VT_CUDA(cudaMalloc(&ts->vnabsRanks, nA * 12 * sizeof(int)));
-        ts->scratchCTAs = 2 * ctx->prop.multiProcessorCount;
+        ts->scratchCTAs = (nmax <= 16 ? 4 : 2) * ctx->prop.multiProcessorCount;
         const size_t per = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
         VT_CUDA(cudaMalloc(&ts->scratch, (size_t)ts->scratchCTAs * per * sizeof(double)));
         tucker_from_dense(ctx, sp);   // whatever the species holds (zeros after vt_species_create)
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ---- multi-GPU: the Tucker state of boundary tets is mirrored into the peers' ghost rows
+struct TuckerIpc {
+    cudaIpcMemHandle_t block;
+    unsigned long long rows, slot;
+    unsigned char pad[48];
+};
+static_assert(sizeof(TuckerIpc) == 128, "Tucker halo handle is 128 bytes");
+
+int vt_tucker_halo_export(vt_ctx* ctx, int species, void* handle)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        TuckerIpc pk;
+        std::memset(&pk, 0, sizeof(pk));
+        VT_CUDA(cudaIpcGetMemHandle(&pk.block, ts.block));
+        pk.rows = ts.rows;
+        pk.slot = ts.slot;
+        std::memcpy(handle, &pk, sizeof(pk));
+    });
+}
+
+int vt_tucker_halo_attach(vt_ctx* ctx, int species, int nPeers, const void* peerHandles)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        if (nPeers != sp.nPeers) throw std::runtime_error("vt_tucker_halo_attach: call vt_halo_attach with the same peers first");
+        const TuckerIpc* pk = static_cast<const TuckerIpc*>(peerHandles);
+        for (int i = 0; i < nPeers; i++) {
+            if (pk[i].slot != ts.slot) throw std::runtime_error("peer Tucker state has a different slot size (maxRank / grid mismatch)");
+            void* base = nullptr;
+            VT_CUDA(cudaIpcOpenMemHandle(&base, pk[i].block, cudaIpcMemLazyEnablePeerAccess));
+            ctx->ipcOpened.push_back(base);
+            tucker_block_pointers(base, (size_t)pk[i].rows, (size_t)pk[i].slot, ts.peerBuf[i], ts.peerRanks[i]);
+        }
+        ts.nPeers = nPeers;
     });
 }
 
@@ -1005,6 +1195,8 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
         TuckerState& ts = state_of(sp);
         if (sp.danglingFaces > 0)
             throw std::runtime_error(std::to_string(sp.danglingFaces) + " boundary faces have no neighbour and no particle BC");
+        if (sp.nPeers > 0 && ts.nPeers != sp.nPeers)
+            throw std::runtime_error("partitioned Tucker species: vt_tucker_halo_attach has not been called");
         ensure_vnabs(ctx, sp, ts);
         TuckerParams P;
         fill_params(ctx, sp, ts, P);
@@ -1016,6 +1208,10 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
         P.dt = dt;
         for (int k = 0; k < 3; k++) P.ext[k] = ext ? ext[k] : 0.0;
         P.wallScale = sp.charge * dt * sp.cellVolume;
+        for (int i = 0; i < kMaxPeers; i++) {
+            P.peerOut[i] = i < ts.nPeers ? ts.peerBuf[i][ts.cur ^ 1] : nullptr;
+            P.peerRout[i] = i < ts.nPeers ? ts.peerRanks[i][ts.cur ^ 1] : nullptr;
+        }
         // VT_TUCKER_PROFILE=1: per-phase clock cycles of thread 0 of CTA 0, printed to stderr
         static const bool profile = getenv("VT_TUCKER_PROFILE") != nullptr;
         long long* profDev = nullptr;

@@ -259,6 +259,7 @@ void vt_ctx_destroy(vt_ctx* ctx)
         cudaFree(sp->density);
         cudaFree(sp->densPartial);
         cudaFree(sp->wall);
+        cudaFree(sp->tetLists);
         vt::tucker_destroy(sp->tucker);
         delete sp;
     }

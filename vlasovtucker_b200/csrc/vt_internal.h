@@ -81,6 +81,8 @@ struct Species {
     std::vector<int32_t> sourceId;
     int danglingFaces = 0;            // boundary faces with neither neighbour nor particle BC
     int fastOnly = -1;                // 1: no tet needs the boundary/halo branches; -1: not evaluated
+    int32_t* tetLists = nullptr;      // device: boundary/halo tets then interior tets (bulk-copy step kernel)
+    int nGeneric = 0, nFast = 0;
     // halo (multi-GPU): peers' ping-pong buffers opened through CUDA IPC
     int nPeers = 0;
     double* peerF[kMaxPeers][2] = {};
@@ -151,6 +153,8 @@ void launch_density(vt_ctx* ctx, Species& sp);
 void tucker_materialize(vt_ctx* ctx, Species& sp);
 // Tucker species: re-compress the dense rows in sp.f[sp.cur] into the Tucker state (precision 0)
 void tucker_from_dense(vt_ctx* ctx, Species& sp);
+// Tucker species, multi-GPU: copy the current slots of the boundary tets into the peers' ghost rows
+void tucker_push_current(vt_ctx* ctx, Species& sp);
 void poisson_destroy(PoissonData* p);
 double* ctx_stage(vt_ctx* ctx, size_t bytes);
 double* ctx_pinned(vt_ctx* ctx, size_t bytes);

@@ -16,7 +16,8 @@ PI = 3.14159265358979323846
 class PartitionedSpecies:
     """A species on one rank of a partitioned mesh: owned + ghost rows, halo wired up."""
 
-    def __init__(self, ctx, lp, dist, n, vmin, vmax, mass, charge, bc_type=None):
+    def __init__(self, ctx, lp, dist, n, vmin, vmax, mass, charge, bc_type=None, tucker=None):
+        """tucker = (comprErr, maxRank) keeps the species in Tucker format (ParticleData<Tucker>)."""
         self.ctx, self.lp, self.dist = ctx, lp, dist
         self.sp = ctx.species_create(n, vmin, vmax, mass, charge)
         nO = len(lp.owned)
@@ -28,6 +29,12 @@ class PartitionedSpecies:
             handles = np.stack([np.frombuffer(gathered[q], np.uint8) for q in lp.peers])
             ctx.halo_attach(self.sp, lp.rank, lp.peers, handles)
             ctx.halo_set_push(self.sp, lp.push_peer, lp.push_row)
+        if tucker is not None:
+            ctx.tucker_enable(self.sp, tucker[0], tucker[1])
+            mine = ctx.tucker_halo_export(self.sp)
+            dist.all_gather_object(gathered, mine.tobytes())
+            if lp.peers:
+                ctx.tucker_halo_attach(self.sp, np.stack([np.frombuffer(gathered[q], np.uint8) for q in lp.peers]))
 
     def fill_ghosts(self):
         """Initial ghost fill: push the current owned boundary rows to the peers."""
@@ -81,3 +88,48 @@ class WeakScaledBox:
             self.ctx.halo_barrier()
         region_ms, _, _ = self.ctx.profile_end()
         return max(region_ms, (time.perf_counter() - t0) * 1e3)
+
+
+class ReplicatedField:
+    """Field solve for a partitioned run.  The Poisson unknowns are one double per tet — 1/N_v of
+    the kinetic state — so every rank solves the *global* system redundantly with the same
+    deterministic kernels (second context holding the global mesh) and keeps E for its own rows:
+    the result is bit-identical on all ranks and to the single-GPU loop.  Per step each rank
+    contributes the charge density of its owned tets (solver.cpp:98-105); that all-gather is the
+    only collective of the coupled loop."""
+
+    def __init__(self, local_device, global_tables, lp, dist, bc_type, bc_value=None, bc_normal_grad=None):
+        self.lp, self.dist = lp, dist
+        self.nT = global_tables.nTets
+        self.g = Context(local_device)
+        self.g.mesh_upload(global_tables)
+        self.g.poisson_setup(bc_type, bc_value, bc_normal_grad)
+        ids = [None] * dist.get_world_size()
+        dist.all_gather_object(ids, np.asarray(lp.owned, np.int64))
+        self.owned_of = ids
+
+    def solve(self, ctx, species, charges, background=None):
+        """rho = sum_s charge_s * Density_s + background on the global mesh, Poisson solve, E of the
+        owned rows into ``ctx``.  Returns (rho, phi, E) of the global mesh."""
+        local = np.zeros(len(self.lp.owned))
+        for sp, q in zip(species, charges):
+            local += q * ctx.density(sp)
+        parts = [None] * self.dist.get_world_size()
+        self.dist.all_gather_object(parts, local)
+        rho = np.zeros(self.nT) if background is None else np.array(background, dtype=np.float64)
+        for ids, p in zip(self.owned_of, parts):
+            rho[ids] += p
+        phi, E = self.g.poisson_solve(rho)
+        ctx.field_set(E[self.lp.owned])
+        return rho, phi, E
+
+    def close(self):
+        self.g.close()
+
+
+def wall_charge_total(ctx, sp, entity, dist):
+    """Absorbed charge of one boundary entity summed over the ranks (solver.cpp:171-178 accumulates
+    it per face; the faces of an entity are spread over the partitions)."""
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, ctx.wall_charge(sp, entity))
+    return float(np.sum(parts))   # fixed rank order: identical on every rank
