@@ -465,7 +465,7 @@ bool launch_full_step_async(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind
     if (D < 2) return false;
     const size_t smem = (size_t)(D + 2) * 5 * PB + fixed;
 
-    if (!ctx->workCounter) VT_CUDA(cudaMalloc(&ctx->workCounter, sizeof(unsigned long long)));
+    if (!ctx->workCounter) VT_CUDA(cudaMalloc(&ctx->workCounter, 2 * sizeof(unsigned long long)));
     AsyncParams P;
     P.s = p;
     P.planeElems = PE;

@@ -27,6 +27,9 @@
 // own(j+1) [centre, i0/i1 neighbours], own(j+2) [i2+1], nbr(j), and prev/cur from registers.
 #include "vt_internal.h"
 
+#include <algorithm>
+#include <cmath>
+
 namespace vt {
 
 namespace {
@@ -281,6 +284,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
 {
     const StepParams& p = P.s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr bool PAIRED = KPT == 2 && NCW == 8;   // see the column mapping in k_full_step_bulk
 
     double cxy[KPT][4][2], hc[4], cz[4];
     bool pairF[4], absF[4], colF[4];
@@ -360,12 +364,16 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
         double tzf[4];
 #pragma unroll
         for (int f = 0; f < 4; f++) tzf[f] = __dmul_rn(cz[f], v2);
+        double2 nxv[KPT];
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
             if (!col[kk].on) continue;
             const double2 nx = lds128(snA + col[kk].evB);
-            const double2 um = lds128(scA + col[kk].dUmB);
-            const double2 up = lds128(scA + col[kk].dUpB);
+            nxv[kk] = nx;
+            // PAIRED: the thread's two columns are neighbours in i1, so each one's i1 neighbour on
+            // that side is the other one's centre value, already in registers
+            const double2 um = (PAIRED && kk == 1) ? cr[0] : lds128(scA + col[kk].dUmB);
+            const double2 up = (PAIRED && kk == 0) ? cr[KPT - 1] : lds128(scA + col[kk].dUpB);
             const double fl = lds64(scA + col[kk].dFlB);
             const double fr = lds64(scA + col[kk].dFrB);
             double2 fa[4];
@@ -420,10 +428,14 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
                     if (pushOn[q]) *reinterpret_cast<double2*>(outp[kk] + pushOff[q]) = o;
             }
             outp[kk] += R.PB;
-            prv[kk] = cr[kk];
-            cr[kk] = nx;
         }
-        v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + j + 1), p.step[2]));
+#pragma unroll
+        for (int kk = 0; kk < KPT; kk++) {
+            if (!col[kk].on) continue;
+            prv[kk] = cr[kk];
+            cr[kk] = nxv[kk];
+        }
+        v2 =__dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + j + 1), p.step[2]));
         __syncwarp();   // every lane is done with own stage sc and neighbour slot nbSlot
         if (lane == 0) {
             mbar_arrive32(R.ownEmpty + scSlot * 8);
@@ -495,7 +507,9 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
     Column col[KPT];
 #pragma unroll
     for (int kk = 0; kk < KPT; kk++) {
-        const int v = tid + kk * NCW * 32;
+        // eight warps x two columns (launched only when the plane is exactly 2 x 256 double2 and n1 is
+        // even): the two columns of a thread are the rows 2m and 2m+1 of the same i0 pair
+        const int v = (KPT == 2 && NCW == 8) ? (tid % p.nvec0) + p.nvec0 * (2 * (tid / p.nvec0) + kk) : tid + kk * NCW * 32;
         col[kk].on = v < P.PV;
         const int cv = col[kk].on ? v : 0;
         const int i0 = (cv % p.nvec0) * 2, i1 = cv / p.nvec0;
@@ -542,14 +556,14 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
 }
 
 template <int KPT, int NCW>
-void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, size_t smem)
+void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, size_t smem, cudaStream_t stream, int maxCTAs)
 {
     if (P.total == 0) return;
-    const int grid = (int)std::min<long long>(P.total, ctx->prop.multiProcessorCount);
+    const int grid = (int)std::min<long long>(P.total, maxCTAs);
     auto launch = [&](auto kern) {
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        VT_CUDA(cudaMemsetAsync(ctx->workCounter, 0, sizeof(unsigned long long), ctx->stream));
-        kern<<<grid, NCW * 32 + 32, smem, ctx->stream>>>(P);
+        VT_CUDA(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), stream));
+        kern<<<grid, NCW * 32 + 32, smem, stream>>>(P);
         ctx->launches++;
     };
     if (allFast) upwind ? launch(k_full_step_bulk<KPT, true, NCW, true>) : launch(k_full_step_bulk<KPT, false, NCW, true>);
@@ -569,7 +583,7 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     if (((size_t)sp.N * 8) % 16) return false;
     const int PV = PE / 2;
     // variant bit 5: eight consumer warps with two columns per thread instead of sixteen with one
-    const bool wide = (ctx->variant & 32) != 0 && PV > 256 && PV <= 512;
+    const bool wide = (ctx->variant & 32) != 0 && PV == 512 && n1 % 2 == 0 && 256 % (n0 / 2) == 0;
     const int ncw = wide ? 8 : 16;
     const int kpt = (PV + ncw * 32 - 1) / (ncw * 32);
     if (kpt > 4) return false;
@@ -607,7 +621,7 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
             VT_CUDA(cudaMemcpy(sp.tetLists, gen.data(), gen.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         }
     }
-    if (!ctx->workCounter) VT_CUDA(cudaMalloc(&ctx->workCounter, sizeof(unsigned long long)));
+    if (!ctx->workCounter) VT_CUDA(cudaMalloc(&ctx->workCounter, 2 * sizeof(unsigned long long)));
     BulkParams P;
     P.s = p;
     P.OD = OD;
@@ -616,22 +630,27 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     P.PV = PV;
     P.queue = ctx->workCounter;
 
-    auto run = [&](const int* list, int nTets, bool allFast) {
+    const int sms = ctx->prop.multiProcessorCount;
+    auto run = [&](const int* list, int nTets, bool allFast, cudaStream_t stream, int maxCTAs, int counter) {
         P.tetList = list;
         P.nTets = nTets;
         P.total = (long long)nTets * p.nChunks;
-        if (wide) launch_cfg<2, 8>(ctx, P, upwind, allFast, smem);
-        else if (kpt == 1) launch_cfg<1, 16>(ctx, P, upwind, allFast, smem);
-        else if (kpt == 2) launch_cfg<2, 16>(ctx, P, upwind, allFast, smem);
-        else if (kpt == 3) launch_cfg<3, 16>(ctx, P, upwind, allFast, smem);
-        else launch_cfg<4, 16>(ctx, P, upwind, allFast, smem);
+        P.queue = ctx->workCounter + counter;
+        if (wide) launch_cfg<2, 8>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 1) launch_cfg<1, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 2) launch_cfg<2, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 3) launch_cfg<3, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else launch_cfg<4, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
     };
     VT_CUDA(cudaEventRecord(e0, ctx->stream));
     if (sp.fastOnly == 1) {
-        run(nullptr, ctx->nOwned, true);
+        run(nullptr, ctx->nOwned, true, ctx->stream, sms, 0);
     } else {
-        run(sp.tetLists, sp.nGeneric, false);
-        run(sp.tetLists + sp.nGeneric, sp.nFast, true);
+        // boundary/halo tets first, then the interior ones, on the same stream.  (Running the first
+        // launch concurrently on a few SMs of a side stream was measured: 32 ms instead of 20 ms per
+        // 2-GPU step — a handful of SMs cannot feed the NVLink stores of all ghost rows.)
+        run(sp.tetLists, sp.nGeneric, false, ctx->stream, sms, 0);
+        run(sp.tetLists + sp.nGeneric, sp.nFast, true, ctx->stream, sms, 1);
     }
     VT_CUDA(cudaEventRecord(e1, ctx->stream));
     VT_CUDA(cudaGetLastError());

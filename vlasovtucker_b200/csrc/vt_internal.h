@@ -129,7 +129,7 @@ struct vt_ctx {
 
     int chunkPlanes = 0, brickTets = 0;
     int variant = 64;   // vt_step_config bits; 64 = choose the step kernel from the velocity grid
-    unsigned long long* workCounter = nullptr;   // device: head of the persistent kernel's work queue
+    unsigned long long* workCounter = nullptr;   // device: heads of the persistent kernels' work queues (2)
 
     vt::PoissonData* poisson = nullptr;
 
