@@ -119,7 +119,8 @@ __device__ void mode_apply(const double* __restrict__ src, double* __restrict__ 
 // them in registers across tiles; G is written symmetric with leading dimension ld = n | 1 (odd, so
 // that both row and column walks are bank-conflict free in the eigen-solver).
 // pairs per thread: 64*65/2 over 256 threads, or 16*17/2 over 128
-template <int T> struct PairsPerThread { static constexpr int value = T == kThreads ? (kMaxN * (kMaxN + 1) / 2 + T - 1) / T : (16 * 17 / 2 + T - 1) / T; };
+// (i <= j) Gram entries per thread for a kernel instance serving grids of up to NM nodes per axis with T threads
+template <int T, int NM> struct PairsPerThread { static constexpr int value = (NM * (NM + 1) / 2 + T - 1) / T; };
 
 struct GramWork {
     double* tile;              // tileCap = (nmax | 1) * nmax doubles
@@ -142,15 +143,15 @@ __device__ void build_pairs(unsigned short* pairs, int nmax)
 
 constexpr int kPrefetch = 4;   // doubles per thread held for the next Gram tile
 
-template <int T>
+template <int T, int NM>
 __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode, double* __restrict__ G, const GramWork& gw)
 {
     const int n = d[mode];
     const int np = pair_count(n);
-    double acc[PairsPerThread<T>::value];
-    int pi[PairsPerThread<T>::value], pj[PairsPerThread<T>::value];
+    double acc[PairsPerThread<T, NM>::value];
+    int pi[PairsPerThread<T, NM>::value], pj[PairsPerThread<T, NM>::value];
 #pragma unroll
-    for (int k = 0; k < PairsPerThread<T>::value; k++) {
+    for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
         acc[k] = 0.0;
         const int q = threadIdx.x + k * T;
         const unsigned short pr = q < np ? gw.pairs[q] : 0;
@@ -162,7 +163,7 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
         // slabs A = X(:, :, i2), n0 x n1; mode 0: G += A A^T, mode 1: G += A^T A
         const int ld = mode == 0 ? n0 : (n0 | 1);
         // the next slab is fetched into registers while the current one is consumed from shared memory
-        const bool pf = M <= kPrefetch * T;
+        const bool pf = M <= (kPrefetch * T);
         double pre[kPrefetch];
         if (pf) {
 #pragma unroll
@@ -191,7 +192,7 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
                 }
             }
 #pragma unroll
-            for (int k = 0; k < PairsPerThread<T>::value; k++) {
+            for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
                 if (threadIdx.x + k * T >= np) break;
                 double s = acc[k];
                 if (mode == 0) {
@@ -211,7 +212,7 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
         // X as an M x n2 matrix B (column a = plane a); G = B^T B over row chunks of Tr rows
         const int ldmax = gw.tileCap / n2;                       // the chunk (ld x n2) has to fit the tile
         const int rowsFit = min(M, (ldmax & 1) ? ldmax : ldmax - 1);
-        const int rowsPf = kPrefetch * T / n2;                    // a chunk the register prefetch can hold
+        const int rowsPf = (kPrefetch * T) / n2;                    // a chunk the register prefetch can hold
         const bool pf = rowsPf >= 8;
         const int rows = pf ? min(rowsFit, rowsPf) : rowsFit;
         const int ld = rows | 1;
@@ -248,7 +249,7 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
                 }
             }
 #pragma unroll
-            for (int k = 0; k < PairsPerThread<T>::value; k++) {
+            for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
                 if (threadIdx.x + k * T >= np) break;
                 const double* a = gw.tile + ld * pi[k];
                 const double* b = gw.tile + ld * pj[k];
@@ -261,7 +262,7 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
     }
     const int ldg = n | 1;
 #pragma unroll
-    for (int k = 0; k < PairsPerThread<T>::value; k++) {
+    for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
         if (threadIdx.x + k * T >= np) break;
         G[pi[k] + ldg * pj[k]] = acc[k];
         G[pj[k] + ldg * pi[k]] = acc[k];
@@ -499,12 +500,12 @@ struct TruncWork {
 // Truncated HOSVD of the dense tensor X (dims d).  Writes the factors to Uout[k] (leading dimension
 // d[k], rcap[k] columns available), the core to coreOut (r0 x r1 x r2 packed), the ranks to rsel.
 // W1/W2 are dense work buffers (>= N doubles each).
-template <int T>
+template <int T, int NM>
 __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int rmax, const int rcap[3], double* const Uout[3],
                                double* coreOut, double* W1, double* W2, const TruncWork& w)
 {
     long long t0 = clock64();
-    for (int k = 0; k < 3; k++) gram_mode<T>(X, d, k, w.G[k], w.gw);
+    for (int k = 0; k < 3; k++) gram_mode<T, NM>(X, d, k, w.G[k], w.gw);
     long long t1 = clock64();
     if (w.prof) w.prof[0] += t1 - t0;
     const int warp = threadIdx.x >> 5;
@@ -634,7 +635,7 @@ __device__ void slot_ptrs(double* base, const TuckerParams& P, double*& core, do
     U[2] = U[1] + (size_t)P.n[1] * P.rcap[1];
 }
 
-template <int T>
+template <int T, int NM>
 __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const TuckerParams P)
 {
     extern __shared__ double sDyn[];   // 3 Gram/eigenvector matrices + one staging tile, (nmax|1)*nmax doubles each
@@ -686,7 +687,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
             slot_ptrs(P.out + (size_t)t * P.slot, P, core, U);
             for (int e = threadIdx.x; e < N; e += blockDim.x) A[e] = P.denseIn[(size_t)t * N + e];
             __syncthreads();
-            hosvd_truncate<T>(A, d, 0.0, P.maxRank, P.rcap, U, core, W1, W2, w);
+            hosvd_truncate<T, NM>(A, d, 0.0, P.maxRank, P.rcap, U, core, W1, W2, w);
             if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
             __syncthreads();
             continue;
@@ -722,7 +723,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
                 double* vs = P.vnabs + ((size_t)t * 4 + f) * P.vslot;
                 double* Uv[3] = {vs + 216, vs + 216 + 6 * d[0], vs + 216 + 6 * (d[0] + d[1])};
                 const int cap6[3] = {min(6, d[0]), min(6, d[1]), min(6, d[2])};
-                hosvd_truncate<T>(A, d, P.epsAbs, 6, cap6, Uv, vs, W1, W2, w);
+                hosvd_truncate<T, NM>(A, d, P.epsAbs, 6, cap6, Uv, vs, W1, W2, w);
                 if (threadIdx.x < 3) P.vnabsRanks[((size_t)t * 4 + f) * 3 + threadIdx.x] = sR[threadIdx.x];
                 __syncthreads();
             }
@@ -783,7 +784,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
             __syncthreads();
             if (w.prof) w.prof[5] += clock64() - tFlux;
             // rhs.Compress(comprErr, maxRank)                                           solver.cpp:182
-            hosvd_truncate<T>(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);
+            hosvd_truncate<T, NM>(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);
             const int r[3] = {sR[0], sR[1], sR[2]};
             reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile, w.prof);
         }
@@ -807,7 +808,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
             for (int e = threadIdx.x; e < N; e += blockDim.x) RHS[e] = W1[e];
             __syncthreads();
             if (w.prof) w.prof[6] += clock64() - tDer;
-            hosvd_truncate<T>(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);   // solver.cpp:199
+            hosvd_truncate<T, NM>(RHS, d, P.eps, P.maxRank, fullcap, Uw, coreW, W1, W2, w);   // solver.cpp:199
             const int r[3] = {sR[0], sR[1], sR[2]};
             reconstruct(coreW, r, Uw, d, RHS, W1, W2, w.gw.tile, w.prof);
         }
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
         {
             double *core, *U[3];
             slot_ptrs(P.out + (size_t)t * P.slot, P, core, U);
-            hosvd_truncate<T>(B, d, P.eps, P.maxRank, P.rcap, U, core, W1, W2, w);
+            hosvd_truncate<T, NM>(B, d, P.eps, P.maxRank, P.rcap, U, core, W1, W2, w);
             if (threadIdx.x < 3) P.rout[3 * t + threadIdx.x] = sR[threadIdx.x];
             const int r[3] = {sR[0], sR[1], sR[2]};
             reconstruct(core, r, U, d, B, W1, W2, w.gw.tile, w.prof);   // Density() sums the rounded tensor (particle_data.cpp:99)
@@ -914,12 +915,16 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
     const size_t smem = (3 * (size_t)(nmax | 1) + std::max(nmax | 1, (nmax + kQB - 1) / kQB * kQB)) * nmax * sizeof(double);
     if (nmax <= 16) {
-        k_tucker<kThreadsSmall><<<grid, kThreadsSmall, smem, ctx->stream>>>(P);
+        k_tucker<kThreadsSmall, 16><<<grid, kThreadsSmall, smem, ctx->stream>>>(P);
+    } else if (nmax <= 32) {
+        if (smem > 32 * 1024)
+            VT_CUDA(cudaFuncSetAttribute(k_tucker<kThreadsSmall, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tucker<kThreadsSmall, 32><<<grid, kThreadsSmall, smem, ctx->stream>>>(P);
     } else {
         if (smem > 32 * 1024)
-            VT_CUDA(cudaFuncSetAttribute(k_tucker<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            VT_CUDA(cudaFuncSetAttribute(k_tucker<kThreads, kMaxN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          4 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
-        k_tucker<kThreads><<<grid, kThreads, smem, ctx->stream>>>(P);
+        k_tucker<kThreads, kMaxN><<<grid, kThreads, smem, ctx->stream>>>(P);
     }
     ctx->launches++;
     VT_CUDA(cudaGetLastError());
@@ -1054,7 +1059,7 @@ int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
         ts->vslot = 216 + 6 * (size_t)(sp.n[0] + sp.n[1] + sp.n[2]);
         VT_CUDA(cudaMalloc(&ts->vnabs, nA * 4 * ts->vslot * sizeof(double)));
         VT_CUDA(cudaMalloc(&ts->vnabsRanks, nA * 12 * sizeof(int)));
-        ts->scratchCTAs = (nmax <= 16 ? 4 : 2) * ctx->prop.multiProcessorCount;
+        ts->scratchCTAs = (nmax <= 32 ? 4 : 2) * ctx->prop.multiProcessorCount;
         const size_t per = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
         VT_CUDA(cudaMalloc(&ts->scratch, (size_t)ts->scratchCTAs * per * sizeof(double)));
         tucker_from_dense(ctx, sp);   // whatever the species holds (zeros after vt_species_create)
