@@ -345,6 +345,7 @@ void launch_density(vt_ctx* ctx, Species& sp)
 void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
 {
     if (ctx->nOwned == 0) return;
+    if (sp.tucker) throw std::runtime_error("vt_step_full: the species is in Tucker format (use vt_step_tucker)");
     if (sp.danglingFaces > 0)
         throw std::runtime_error(std::to_string(sp.danglingFaces) +
                                  " boundary faces have no neighbour and no particle BC (Absorbing/Free/Source); "

@@ -69,7 +69,6 @@ struct AsyncParams {
     int planeElems;   // n0*n1
     int PV;           // double2 per plane
     unsigned long long* counter;   // work queue head (zeroed before the launch)
-    int debug;
 };
 
 __device__ __forceinline__ void decode_item(const StepParams& p, long long w, long long total, ItemDesc& it)
@@ -471,7 +470,6 @@ bool launch_full_step_async(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind
     P.planeElems = PE;
     P.PV = PV;
     P.counter = ctx->workCounter;
-    P.debug = std::getenv("VT_ASYNC_DEBUG") ? std::atoi(std::getenv("VT_ASYNC_DEBUG")) : 0;
     const long long total = (long long)ctx->nOwned * p.nChunks;
     const int grid = (int)std::min<long long>(total, ctx->prop.multiProcessorCount);
 

@@ -421,7 +421,9 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
                 accDens = __dadd_rn(accDens, out[u]);
             }
             const double2 o = make_double2(out[0], out[1]);
-            *reinterpret_cast<double2*>(outp[kk]) = o;
+            // streaming store (evict-first): the new state is not read again in this launch and should
+            // not push the step-n rows, which four neighbours still want, out of L2
+            __stcs(reinterpret_cast<double2*>(outp[kk]), o);
             if (GENERIC) {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
@@ -649,8 +651,19 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
         // boundary/halo tets first, then the interior ones, on the same stream.  (Running the first
         // launch concurrently on a few SMs of a side stream was measured: 32 ms instead of 20 ms per
         // 2-GPU step — a handful of SMs cannot feed the NVLink stores of all ghost rows.)
-        run(sp.tetLists, sp.nGeneric, false, ctx->stream, sms, 0);
-        run(sp.tetLists + sp.nGeneric, sp.nFast, true, ctx->stream, sms, 1);
+        // With many halo tets (>= 4 % of the partition, or VT_STEP_MIXED=1) one launch takes the whole
+        // list — boundary tets at the head of the queue, interior tets behind them in the same
+        // kernel — so that the NVLink stores of the ghost rows drain behind the interior work instead
+        // of holding up the end of a separate first launch; the price is the slightly slower
+        // interior path of the kernel that carries the boundary branches.
+        static const int mixedEnv = std::getenv("VT_STEP_MIXED") ? std::atoi(std::getenv("VT_STEP_MIXED")) : -1;
+        const bool mixed = mixedEnv >= 0 ? mixedEnv != 0 : (long long)sp.nGeneric * 25 >= ctx->nOwned;
+        if (mixed) {
+            run(sp.tetLists, sp.nGeneric + sp.nFast, false, ctx->stream, sms, 0);
+        } else {
+            run(sp.tetLists, sp.nGeneric, false, ctx->stream, sms, 0);
+            run(sp.tetLists + sp.nGeneric, sp.nFast, true, ctx->stream, sms, 1);
+        }
     }
     VT_CUDA(cudaEventRecord(e1, ctx->stream));
     VT_CUDA(cudaGetLastError());
