@@ -437,7 +437,13 @@ __device__ void eig_sym_warp(double* V, int n, int ld, double* dv, double* ev)
                     // r = hypot(p, e_i), s = e_i / r, c = p / r.  Scaling by a power of two (exact) keeps the
                     // squares of the subnormal noise entries of a rank-deficient Gram matrix from
                     // underflowing; one reciprocal square root replaces the divisions.
-                    {
+                    const double q2plain = fma(p, p, ei * ei);
+                    if (q2plain > 1e-280 && q2plain < 1e280) {   // the usual case: no scaling needed
+                        const double qinv = rsqrt(q2plain);
+                        r = q2plain * qinv;
+                        s = ei * qinv;
+                        c = p * qinv;
+                    } else {
                         const double mx = fmax(fabs(p), fabs(ei));
                         if (mx == 0.0) {
                             r = 0.0;
