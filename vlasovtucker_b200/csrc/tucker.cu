@@ -123,7 +123,7 @@ __device__ void mode_apply(const double* __restrict__ src, double* __restrict__ 
 template <int T, int NM> struct PairsPerThread { static constexpr int value = (NM * (NM + 1) / 2 + T - 1) / T; };
 
 struct GramWork {
-    double* tile;              // tileCap = (nmax | 1) * nmax doubles
+    double* tile;              // two buffers of tileCap doubles each
     int tileCap;
     const unsigned short* pairs;   // pair q -> i | (j << 8), i <= j, for n = nmax (prefix valid for smaller n)
 };
@@ -141,8 +141,20 @@ __device__ void build_pairs(unsigned short* pairs, int nmax)
     __syncthreads();
 }
 
-constexpr int kPrefetch = 4;   // doubles per thread held for the next Gram tile
+// 8-byte asynchronous copy global -> shared (the padded tile layouts are only 8-byte aligned)
+__device__ __forceinline__ void cp_async8(double* dst, const double* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
+// The tile is double buffered (two halves of tileCap doubles): while the pairs of one slab/chunk are
+// accumulated from shared memory, cp.async brings the next one in.
 template <int T, int NM>
 __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode, double* __restrict__ G, const GramWork& gw)
 {
@@ -162,46 +174,33 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
     if (mode == 0 || mode == 1) {
         // slabs A = X(:, :, i2), n0 x n1; mode 0: G += A A^T, mode 1: G += A^T A
         const int ld = mode == 0 ? n0 : (n0 | 1);
-        // the next slab is fetched into registers while the current one is consumed from shared memory
-        const bool pf = M <= (kPrefetch * T);
-        double pre[kPrefetch];
-        if (pf) {
-#pragma unroll
-            for (int q = 0; q < kPrefetch; q++) {
-                const int e = threadIdx.x + q * T;
-                pre[q] = e < M ? X[e] : 0.0;
-            }
-        }
-        for (int i2 = 0; i2 < n2; i2++) {
+        auto issue = [&](int i2) {
             const double* slab = X + (size_t)i2 * M;
-            if (pf) {
-#pragma unroll
-                for (int q = 0; q < kPrefetch; q++) {
-                    const int e = threadIdx.x + q * T;
-                    if (e < M) gw.tile[(e % n0) + ld * (e / n0)] = pre[q];
-                }
+            double* t = gw.tile + (size_t)(i2 & 1) * gw.tileCap;
+            for (int e = threadIdx.x; e < M; e += T) cp_async8(t + (e % n0) + ld * (e / n0), slab + e);
+            cp_async_commit();
+        };
+        issue(0);
+        for (int i2 = 0; i2 < n2; i2++) {
+            if (i2 + 1 < n2) {
+                issue(i2 + 1);
+                cp_async_wait<1>();
             } else {
-                for (int e = threadIdx.x; e < M; e += blockDim.x) gw.tile[(e % n0) + ld * (e / n0)] = slab[e];
+                cp_async_wait<0>();
             }
             __syncthreads();
-            if (pf && i2 + 1 < n2) {
-#pragma unroll
-                for (int q = 0; q < kPrefetch; q++) {
-                    const int e = threadIdx.x + q * T;
-                    pre[q] = e < M ? slab[M + e] : 0.0;
-                }
-            }
+            const double* tile = gw.tile + (size_t)(i2 & 1) * gw.tileCap;
 #pragma unroll
             for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
                 if (threadIdx.x + k * T >= np) break;
                 double s = acc[k];
                 if (mode == 0) {
-                    const double* a = gw.tile + pi[k];
-                    const double* b = gw.tile + pj[k];
+                    const double* a = tile + pi[k];
+                    const double* b = tile + pj[k];
                     for (int c = 0; c < n1; c++) s = fma(a[ld * c], b[ld * c], s);
                 } else {
-                    const double* a = gw.tile + ld * pi[k];
-                    const double* b = gw.tile + ld * pj[k];
+                    const double* a = tile + ld * pi[k];
+                    const double* b = tile + ld * pj[k];
                     for (int r = 0; r < n0; r++) s = fma(a[r], b[r], s);
                 }
                 acc[k] = s;
@@ -209,50 +208,36 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
             __syncthreads();
         }
     } else {
-        // X as an M x n2 matrix B (column a = plane a); G = B^T B over row chunks of Tr rows
-        const int ldmax = gw.tileCap / n2;                       // the chunk (ld x n2) has to fit the tile
-        const int rowsFit = min(M, (ldmax & 1) ? ldmax : ldmax - 1);
-        const int rowsPf = (kPrefetch * T) / n2;                    // a chunk the register prefetch can hold
-        const bool pf = rowsPf >= 8;
-        const int rows = pf ? min(rowsFit, rowsPf) : rowsFit;
+        // X as an M x n2 matrix B (column a = plane a); G = B^T B over row chunks
+        const int ldmax = gw.tileCap / n2;                       // the chunk (ld x n2) has to fit half the tile
+        const int rows = min(M, (ldmax & 1) ? ldmax : ldmax - 1);
         const int ld = rows | 1;
-        double pre[kPrefetch];
-        if (pf) {
-            const int nr = min(rows, M);
-#pragma unroll
-            for (int q = 0; q < kPrefetch; q++) {
-                const int e = threadIdx.x + q * T;
-                pre[q] = e < nr * n2 ? X[(size_t)(e % nr) + (size_t)M * (e / nr)] : 0.0;
+        const int nChunks = (M + rows - 1) / rows;
+        auto issue = [&](int c) {
+            const int r0 = c * rows, nr = min(rows, M - r0);
+            double* t = gw.tile + (size_t)(c & 1) * gw.tileCap;
+            for (int e = threadIdx.x; e < nr * n2; e += T) {
+                const int r = e % nr, a = e / nr;
+                cp_async8(t + r + ld * a, X + (size_t)r0 + r + (size_t)M * a);
             }
-        }
-        for (int r0 = 0; r0 < M; r0 += rows) {
-            const int nr = min(rows, M - r0);
-            if (pf) {
-#pragma unroll
-                for (int q = 0; q < kPrefetch; q++) {
-                    const int e = threadIdx.x + q * T;
-                    if (e < nr * n2) gw.tile[(e % nr) + ld * (e / nr)] = pre[q];
-                }
+            cp_async_commit();
+        };
+        issue(0);
+        for (int c = 0; c < nChunks; c++) {
+            if (c + 1 < nChunks) {
+                issue(c + 1);
+                cp_async_wait<1>();
             } else {
-                for (int e = threadIdx.x; e < nr * n2; e += blockDim.x) {
-                    const int r = e % nr, a = e / nr;
-                    gw.tile[r + ld * a] = X[(size_t)r0 + r + (size_t)M * a];
-                }
+                cp_async_wait<0>();
             }
             __syncthreads();
-            if (pf && r0 + rows < M) {
-                const int rn = r0 + rows, nrn = min(rows, M - rn);
-#pragma unroll
-                for (int q = 0; q < kPrefetch; q++) {
-                    const int e = threadIdx.x + q * T;
-                    pre[q] = e < nrn * n2 ? X[(size_t)rn + (e % nrn) + (size_t)M * (e / nrn)] : 0.0;
-                }
-            }
+            const int nr = min(rows, M - c * rows);
+            const double* tile = gw.tile + (size_t)(c & 1) * gw.tileCap;
 #pragma unroll
             for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
                 if (threadIdx.x + k * T >= np) break;
-                const double* a = gw.tile + ld * pi[k];
-                const double* b = gw.tile + ld * pj[k];
+                const double* a = tile + ld * pi[k];
+                const double* b = tile + ld * pj[k];
                 double s = acc[k];
                 for (int r = 0; r < nr; r++) s = fma(a[r], b[r], s);
                 acc[k] = s;
@@ -919,7 +904,7 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     if (ctx->nOwned == 0) return;
     const int grid = std::min(ctx->nOwned, ts.scratchCTAs);
     const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
-    const size_t smem = (3 * (size_t)(nmax | 1) + std::max(nmax | 1, (nmax + kQB - 1) / kQB * kQB)) * nmax * sizeof(double);
+    const size_t smem = (3 * (size_t)(nmax | 1) + 2 * std::max(nmax | 1, (nmax + kQB - 1) / kQB * kQB)) * nmax * sizeof(double);
     if (nmax <= 16) {
         k_tucker<kThreadsSmall, 16><<<grid, kThreadsSmall, smem, ctx->stream>>>(P);
     } else if (nmax <= 32) {
@@ -929,7 +914,7 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     } else {
         if (smem > 32 * 1024)
             VT_CUDA(cudaFuncSetAttribute(k_tucker<kThreads, kMaxN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         4 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
+                                         5 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
         k_tucker<kThreads, kMaxN><<<grid, kThreads, smem, ctx->stream>>>(P);
     }
     ctx->launches++;
