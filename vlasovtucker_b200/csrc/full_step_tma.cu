@@ -278,7 +278,7 @@ struct ConsRings {
     uint32_t odMask, odShift, sMask, sShift;
 };
 
-template <int KPT, bool UPWIND, bool GENERIC, int NCW>
+template <int KPT, bool UPWIND, bool GENERIC, int NCW, int SN>
 __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRings& R, const ItemHdr& cur, const TetRec& rec,
                                              uint32_t& cOwn, uint32_t& cNbr, const Column (&col)[KPT])
 {
@@ -350,46 +350,68 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
 #pragma unroll
     for (int kk = 0; kk < KPT; kk++) cr[kk] = lds128(scA + col[kk].evB);
 
-    double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)cur.pl0, p.step[2]));
-    for (int j = 0; j < cur.npl; j++) {
+    // Per-thread byte offsets of the stencil operands.  With a compile-time plane shape (SN x SN) and
+    // paired columns the second column is the first plus one row, so most addresses become
+    // register + immediate.
+    constexpr bool SPEC = SN > 0 && PAIRED;
+    const uint32_t PB = SPEC ? (uint32_t)(SN * SN * 8) : R.PB;
+    uint32_t oEv[KPT], oUm[KPT], oUp[KPT], oFl[KPT], oFr[KPT];
+#pragma unroll
+    for (int kk = 0; kk < KPT; kk++) {
+        oEv[kk] = (SPEC && kk == 1) ? col[0].evB + SN * 8 : col[kk].evB;
+        oUm[kk] = col[kk].dUmB;
+        oUp[kk] = col[kk].dUpB;
+        oFl[kk] = (SPEC && kk == 1) ? col[0].dFlB + SN * 8 : col[kk].dFlB;
+        oFr[kk] = (SPEC && kk == 1) ? col[0].dFrB + SN * 8 : col[kk].dFrB;
+    }
+    if (SPEC) {
+#pragma unroll
+        for (int kk = 1; kk < KPT; kk++) outp[kk] = outp[0] + SN * 8;
+    }
+
+    double2 nxt[KPT];
+    int j = 0;
+    // One plane: pv/cv hold planes j-1 and j of the thread's columns, nv receives plane j+1.  The
+    // plane loop below calls it with the three register sets rotating, so no values are moved.
+    auto plane = [&](const double2 (&pv)[KPT], const double2 (&cv)[KPT], double2 (&nv)[KPT]) {
         const uint32_t snSlot = cOwn & R.odMask;
         mbar_wait32(R.ownFull + snSlot * 8, (cOwn >> R.odShift) & 1u);
-        const uint32_t snA = R.own + snSlot * R.PB;       // plane j+1
+        const uint32_t snA = R.own + snSlot * PB;       // plane j+1
         cOwn++;
         const uint32_t nbSlot = cNbr & R.sMask;
         mbar_wait32(R.nbrFull + nbSlot * 8, (cNbr >> R.sShift) & 1u);
-        const uint32_t sbA = R.nbr + nbSlot * 4 * R.PB;
+        const uint32_t sbA = R.nbr + nbSlot * 4 * PB;
         cNbr++;
 
+        const double v2 = __dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + j), p.step[2]));
         double tzf[4];
 #pragma unroll
         for (int f = 0; f < 4; f++) tzf[f] = __dmul_rn(cz[f], v2);
-        double2 nxv[KPT];
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
             if (!col[kk].on) continue;
-            const double2 nx = lds128(snA + col[kk].evB);
-            nxv[kk] = nx;
+            const double2 nx = lds128(snA + oEv[kk]);
+            nv[kk] = nx;
             // PAIRED: the thread's two columns are neighbours in i1, so each one's i1 neighbour on
             // that side is the other one's centre value, already in registers
-            const double2 um = (PAIRED && kk == 1) ? cr[0] : lds128(scA + col[kk].dUmB);
-            const double2 up = (PAIRED && kk == 0) ? cr[KPT - 1] : lds128(scA + col[kk].dUpB);
-            const double fl = lds64(scA + col[kk].dFlB);
-            const double fr = lds64(scA + col[kk].dFrB);
+            const double2 um = (PAIRED && kk == 1) ? cv[0] : lds128(scA + oUm[kk]);
+            const double2 up = (PAIRED && kk == 0) ? cv[KPT - 1] : lds128(scA + oUp[kk]);
+            const double fl = lds64(scA + oFl[kk]);
+            const double fr = lds64(scA + oFr[kk]);
             double2 fa[4];
             {
-                uint32_t a = sbA + col[kk].evB;
+                uint32_t a = sbA + oEv[kk];
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
                     fa[f] = (!GENERIC || pairF[f]) ? lds128(a) : make_double2(0.0, 0.0);
-                    a += R.PB;
+                    a += PB;
                 }
             }
-            const double fcv[2] = {cr[kk].x, cr[kk].y};
-            const double xm[2] = {fl, cr[kk].x};
-            const double xp[2] = {cr[kk].y, fr};
+            const double fcv[2] = {cv[kk].x, cv[kk].y};
+            const double xm[2] = {fl, cv[kk].x};
+            const double xp[2] = {cv[kk].y, fr};
             const double y1m[2] = {um.x, um.y}, y1p[2] = {up.x, up.y};
-            const double z2m[2] = {prv[kk].x, prv[kk].y}, z2p[2] = {nx.x, nx.y};
+            const double z2m[2] = {pv[kk].x, pv[kk].y}, z2p[2] = {nx.x, nx.y};
             double out[2];
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -429,15 +451,8 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
                 for (int q = 0; q < 4; q++)
                     if (pushOn[q]) *reinterpret_cast<double2*>(outp[kk] + pushOff[q]) = o;
             }
-            outp[kk] += R.PB;
+            outp[kk] += PB;
         }
-#pragma unroll
-        for (int kk = 0; kk < KPT; kk++) {
-            if (!col[kk].on) continue;
-            prv[kk] = cr[kk];
-            cr[kk] = nxv[kk];
-        }
-        v2 =__dadd_rn(p.vmin[2], __dmul_rn((double)(cur.pl0 + j + 1), p.step[2]));
         __syncwarp();   // every lane is done with own stage sc and neighbour slot nbSlot
         if (lane == 0) {
             mbar_arrive32(R.ownEmpty + scSlot * 8);
@@ -445,6 +460,15 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
         }
         scA = snA;
         scSlot = snSlot;
+        j++;
+    };
+    while (true) {
+        plane(prv, cr, nxt);
+        if (j == cur.npl) break;
+        plane(cr, nxt, prv);
+        if (j == cur.npl) break;
+        plane(nxt, prv, cr);
+        if (j == cur.npl) break;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive32(R.ownEmpty + scSlot * 8);   // the last own stage (plane pl0+npl)
@@ -464,7 +488,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
     }
 }
 
-template <int KPT, bool UPWIND, int NCW, bool ALLFAST>
+template <int KPT, bool UPWIND, int NCW, bool ALLFAST, int SN>
 __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkParams P)
 {
     const StepParams& p = P.s;
@@ -544,12 +568,12 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
         if (cur.tet < 0) break;
         const TetRec& rec = sm.rec[cItem.slot];
         if (ALLFAST) {
-            item_compute<KPT, UPWIND, false, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+            item_compute<KPT, UPWIND, false, NCW, SN>(P, R, cur, rec, cOwn, cNbr, col);
         } else {
             const bool fast = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]) &&
                               rec.pushPeer[0] < 0;
-            if (fast) item_compute<KPT, UPWIND, false, NCW>(P, R, cur, rec, cOwn, cNbr, col);
-            else item_compute<KPT, UPWIND, true, NCW>(P, R, cur, rec, cOwn, cNbr, col);
+            if (fast) item_compute<KPT, UPWIND, false, NCW, SN>(P, R, cur, rec, cOwn, cNbr, col);
+            else item_compute<KPT, UPWIND, true, NCW, SN>(P, R, cur, rec, cOwn, cNbr, col);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.itemEmpty + cItem.slot);
@@ -557,7 +581,7 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
     }
 }
 
-template <int KPT, int NCW>
+template <int KPT, int NCW, int SN>
 void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, size_t smem, cudaStream_t stream, int maxCTAs)
 {
     if (P.total == 0) return;
@@ -568,8 +592,8 @@ void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, siz
         kern<<<grid, NCW * 32 + 32, smem, stream>>>(P);
         ctx->launches++;
     };
-    if (allFast) upwind ? launch(k_full_step_bulk<KPT, true, NCW, true>) : launch(k_full_step_bulk<KPT, false, NCW, true>);
-    else upwind ? launch(k_full_step_bulk<KPT, true, NCW, false>) : launch(k_full_step_bulk<KPT, false, NCW, false>);
+    if (allFast) upwind ? launch(k_full_step_bulk<KPT, true, NCW, true, SN>) : launch(k_full_step_bulk<KPT, false, NCW, true, SN>);
+    else upwind ? launch(k_full_step_bulk<KPT, true, NCW, false, SN>) : launch(k_full_step_bulk<KPT, false, NCW, false, SN>);
 }
 
 }  // namespace
@@ -638,11 +662,12 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
         P.nTets = nTets;
         P.total = (long long)nTets * p.nChunks;
         P.queue = ctx->workCounter + counter;
-        if (wide) launch_cfg<2, 8>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else if (kpt == 1) launch_cfg<1, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else if (kpt == 2) launch_cfg<2, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else if (kpt == 3) launch_cfg<3, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else launch_cfg<4, 16>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        if (wide && n0 == 32 && n1 == 32) launch_cfg<2, 8, 32>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (wide) launch_cfg<2, 8, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 1) launch_cfg<1, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 2) launch_cfg<2, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 3) launch_cfg<3, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else launch_cfg<4, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
     };
     VT_CUDA(cudaEventRecord(e0, ctx->stream));
     if (sp.fastOnly == 1) {
