@@ -89,3 +89,43 @@ def test_reference_drivers_compile_unchanged_and_known_answers(host_lib):
     assert len(blocks) == 10 and all(b.size == 45 for b in blocks)
     for b in blocks[1:]:
         assert np.abs(b - blocks[0]).max() < 1e-5      # printed with 6 significant digits
+
+
+def test_host_tucker_class_matches_oracle(oracle_mod, host_lib, tmp_path):
+    """The user-facing Tucker value class of the host API against the oracle's restated tucker.cpp:
+    construction, operator+, scalar and Hadamard products, Compress, Sum — ranks equal, tensors to
+    1e-12 (singular-vector signs are implementation defined, so only reconstructions compare)."""
+    exe = os.path.join(BUILD, "tucker_dump")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", f"-I{HOST}", f"-I{HOST}/standin", "-o", exe,
+                           os.path.join(ROOT, "tests", "cpp", "tucker_dump.cpp"), f"-L{ROOT}/vlasovtucker_b200/lib",
+                           "-lvlasov_tucker", "-lvt_b200", "-Wl,-rpath," + os.path.join(ROOT, "vlasovtucker_b200", "lib")])
+    n, eps, rmax = (9, 7, 6), 1e-6, 5
+    ax = [np.linspace(-1, 1, k) for k in n]
+
+    def smooth(c, w):
+        return np.exp(-(((ax[0][:, None, None] - c[0]) / w) ** 2 + ((ax[1][None, :, None] - c[1]) / w) ** 2
+                        + ((ax[2][None, None, :] - c[2]) / w) ** 2 + 0.4 * ax[0][:, None, None] * ax[2][None, None, :]))
+    a = smooth((0.1, -0.2, 0.3), 0.6) + 0.3 * smooth((-0.5, 0.4, 0.0), 0.4)
+    b = smooth((-0.2, 0.1, -0.1), 0.8)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    np.concatenate([a.ravel(order="F"), b.ravel(order="F")]).tofile(fin)
+    subprocess.check_call([exe, fin, fout] + [str(k) for k in n] + [str(eps), str(rmax)])
+    buf = np.fromfile(fout)
+    N = a.size
+    recs = [(tuple(int(x) for x in buf[i:i + 3]), buf[i + 3:i + 3 + N].reshape(n, order="F"), buf[i + 3 + N])
+            for i in range(0, buf.size, N + 4)]
+    assert len(recs) == 5
+    T = oracle_mod.TuckerObj
+    ta, tb = T.from_full(a, eps, rmax), T.from_full(b)
+    want = [ta.clone()]
+    s = ta.clone().axpy(0.7, tb)
+    want.append(s.clone())
+    want.append(s.clone().compress(eps, rmax))
+    h = ta.clone().hadamard(tb)
+    want.append(h.clone())
+    want.append(h.clone().axpy(-0.25, ta).compress(eps, rmax))
+    for k, ((ranks, rec, total), w) in enumerate(zip(recs, want)):
+        assert ranks == w.ranks(), k
+        ref = w.reconstructed()
+        assert np.abs(rec - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()), k
+        assert abs(total - w.sum()) <= 1e-11 * max(1.0, abs(w.sum())), k

@@ -676,13 +676,12 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
         // boundary/halo tets first, then the interior ones, on the same stream.  (Running the first
         // launch concurrently on a few SMs of a side stream was measured: 32 ms instead of 20 ms per
         // 2-GPU step — a handful of SMs cannot feed the NVLink stores of all ghost rows.)
-        // With many halo tets (>= 4 % of the partition, or VT_STEP_MIXED=1) one launch takes the whole
-        // list — boundary tets at the head of the queue, interior tets behind them in the same
-        // kernel — so that the NVLink stores of the ghost rows drain behind the interior work instead
-        // of holding up the end of a separate first launch; the price is the slightly slower
-        // interior path of the kernel that carries the boundary branches.
-        static const int mixedEnv = std::getenv("VT_STEP_MIXED") ? std::atoi(std::getenv("VT_STEP_MIXED")) : -1;
-        const bool mixed = mixedEnv >= 0 ? mixedEnv != 0 : (long long)sp.nGeneric * 25 >= ctx->nOwned;
+        // VT_STEP_MIXED=1 (experiment): one launch over the whole list — boundary tets at the head of
+        // the queue, interior tets behind them in the same kernel, so that the NVLink stores drain
+        // behind the interior work.  Measured slower than the two launches at every N (8 GPUs: 23.7
+        // against 22.8 ms per step): the interior path of the kernel that carries the boundary
+        // branches costs more than the overlap gains.
+        static const bool mixed = std::getenv("VT_STEP_MIXED") && std::atoi(std::getenv("VT_STEP_MIXED")) != 0;
         if (mixed) {
             run(sp.tetLists, sp.nGeneric + sp.nFast, false, ctx->stream, sms, 0);
         } else {
