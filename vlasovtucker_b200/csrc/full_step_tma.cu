@@ -20,6 +20,12 @@
 // i2 keeping the own-row values prev/cur/next in registers; the i0 and i1 stencil neighbours and
 // the four neighbour tets' values come from shared memory.
 //
+// Instances: 16 consumer warps x KPT columns per thread (planes of any even n0 up to 2048 double2), or
+// eight warps x two i1-adjacent columns when the plane is exactly 512 double2, with the 32x32 shape of
+// the bench grid known at compile time.  Tets that need boundary-condition or halo-push code are
+// launched first over their own list, the interior ones after them with those branches compiled
+// out; all instances use explicit roundings so that they produce the same bits.
+//
 // Stage stream of one item with npl planes starting at pl0 (periodic in i2, solver.cpp:380-389):
 //   own stage s = 0 .. npl+1  : plane pl0-1+s of the tet's own row          (ring of OD planes)
 //   nbr stage j = 0 .. npl-1  : plane pl0+j of the (up to) four neighbours  (ring of S x 4 planes)

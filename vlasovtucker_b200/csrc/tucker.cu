@@ -115,28 +115,35 @@ __device__ void mode_apply(const double* __restrict__ src, double* __restrict__ 
 }
 
 // ---- Gram matrices of the three unfoldings, G_k = X_(k) X_(k)^T, accumulated from shared-memory
-// tiles.  Each thread owns a fixed set of (i <= j) entries (pair table in shared memory) and keeps
-// them in registers across tiles; G is written symmetric with leading dimension ld = n | 1 (odd, so
-// that both row and column walks are bank-conflict free in the eigen-solver).
-// pairs per thread: 64*65/2 over 256 threads, or 16*17/2 over 128
-// (i <= j) Gram entries per thread for a kernel instance serving grids of up to NM nodes per axis with T threads
-template <int T, int NM> struct PairsPerThread { static constexpr int value = (NM * (NM + 1) / 2 + T - 1) / T; };
+// tiles.  The (i <= j) entries of a column j are cut into groups of kGB consecutive i; a thread owns
+// a fixed set of groups (table in shared memory) and keeps their sums in registers across tiles:
+// one operand b_j feeds kGB FMAs, 1.25 shared loads per FMA instead of 2.  G is written symmetric
+// with leading dimension ld = n | 1 (odd, so that both row and column walks are bank-conflict free
+// in the eigen-solver).
+constexpr int kGB = 4;
+// number of groups of an n x n Gram matrix: sum_j ceil((j + 1) / kGB)
+__host__ __device__ constexpr int gram_groups(int n)
+{
+    int g = 0;
+    for (int j = 0; j < n; j++) g += (j + kGB) / kGB;
+    return g;
+}
+// groups per thread for a kernel instance serving grids of up to NM nodes per axis with T threads
+template <int T, int NM> struct GroupsPerThread { static constexpr int value = (gram_groups(NM) + T - 1) / T; };
 
 struct GramWork {
     double* tile;              // two buffers of tileCap doubles each
     int tileCap;
-    const unsigned short* pairs;   // pair q -> i | (j << 8), i <= j, for n = nmax (prefix valid for smaller n)
+    const unsigned short* groups;   // group q -> i0 | (j << 8); enumerated column by column, so the
+                                    // first gram_groups(n) entries are the groups of any n <= nmax
 };
 
-__device__ __forceinline__ int pair_count(int n) { return n * (n + 1) / 2; }
-
-// pairs are enumerated column by column: (0,0), (0,1), (1,1), (0,2), ... so the first n(n+1)/2
-// entries of the table built for nmax are exactly the pairs of any n <= nmax
-__device__ void build_pairs(unsigned short* pairs, int nmax)
+__device__ void build_groups(unsigned short* groups, int nmax)
 {
     for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
-        const int base = j * (j + 1) / 2;
-        for (int i = 0; i <= j; i++) pairs[base + i] = (unsigned short)(i | (j << 8));
+        int base = 0;
+        for (int c = 0; c < j; c++) base += (c + kGB) / kGB;
+        for (int i0 = 0; i0 <= j; i0 += kGB) groups[base + i0 / kGB] = (unsigned short)(i0 | (j << 8));
     }
     __syncthreads();
 }
@@ -153,24 +160,43 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// The tile is double buffered (two halves of tileCap doubles): while the pairs of one slab/chunk are
-// accumulated from shared memory, cp.async brings the next one in.
+// The tile is double buffered (two halves of tileCap doubles): while the groups of one slab/chunk
+// are accumulated from shared memory, cp.async brings the next one in.
 template <int T, int NM>
 __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode, double* __restrict__ G, const GramWork& gw)
 {
+    constexpr int GPT = GroupsPerThread<T, NM>::value;
     const int n = d[mode];
-    const int np = pair_count(n);
-    double acc[PairsPerThread<T, NM>::value];
-    int pi[PairsPerThread<T, NM>::value], pj[PairsPerThread<T, NM>::value];
+    const int ng = gram_groups(n);
+    double acc[GPT][kGB];
+    int gi[GPT], gj[GPT], gc[GPT];   // first row, column, rows in the group (0: no group)
 #pragma unroll
-    for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
-        acc[k] = 0.0;
+    for (int k = 0; k < GPT; k++) {
+#pragma unroll
+        for (int u = 0; u < kGB; u++) acc[k][u] = 0.0;
         const int q = threadIdx.x + k * T;
-        const unsigned short pr = q < np ? gw.pairs[q] : 0;
-        pi[k] = pr & 255;
-        pj[k] = pr >> 8;
+        const unsigned short e = q < ng ? gw.groups[q] : 0;
+        gi[k] = e & 255;
+        gj[k] = e >> 8;
+        gc[k] = q < ng ? min(kGB, gj[k] + 1 - gi[k]) : 0;
     }
     const int n0 = d[0], n1 = d[1], n2 = d[2], M = n0 * n1;
+    // accumulate one tile: element (row r of operand i) sits at tile[aStep * r + aOff(i)]
+    auto accumulate = [&](const double* tile, int len, int rowStride, int colStride) {
+#pragma unroll
+        for (int k = 0; k < GPT; k++) {
+            if (gc[k] == 0) continue;
+            const double* b = tile + colStride * gj[k];
+            int off[kGB];   // rows past the end of a short group repeat its last row (their sums are dropped)
+#pragma unroll
+            for (int u = 0; u < kGB; u++) off[u] = colStride * (gi[k] + min(u, gc[k] - 1));
+            for (int r = 0; r < len; r++) {
+                const double bv = b[rowStride * r];
+#pragma unroll
+                for (int u = 0; u < kGB; u++) acc[k][u] = fma(tile[rowStride * r + off[u]], bv, acc[k][u]);
+            }
+        }
+    };
     if (mode == 0 || mode == 1) {
         // slabs A = X(:, :, i2), n0 x n1; mode 0: G += A A^T, mode 1: G += A^T A
         const int ld = mode == 0 ? n0 : (n0 | 1);
@@ -190,21 +216,8 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
             }
             __syncthreads();
             const double* tile = gw.tile + (size_t)(i2 & 1) * gw.tileCap;
-#pragma unroll
-            for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
-                if (threadIdx.x + k * T >= np) break;
-                double s = acc[k];
-                if (mode == 0) {
-                    const double* a = tile + pi[k];
-                    const double* b = tile + pj[k];
-                    for (int c = 0; c < n1; c++) s = fma(a[ld * c], b[ld * c], s);
-                } else {
-                    const double* a = tile + ld * pi[k];
-                    const double* b = tile + ld * pj[k];
-                    for (int r = 0; r < n0; r++) s = fma(a[r], b[r], s);
-                }
-                acc[k] = s;
-            }
+            if (mode == 0) accumulate(tile, n1, ld, 1);   // operand i = row i of A: stride ld along the sum
+            else accumulate(tile, n0, 1, ld);             // operand i = column i of A
             __syncthreads();
         }
     } else {
@@ -231,26 +244,19 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
                 cp_async_wait<0>();
             }
             __syncthreads();
-            const int nr = min(rows, M - c * rows);
-            const double* tile = gw.tile + (size_t)(c & 1) * gw.tileCap;
-#pragma unroll
-            for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
-                if (threadIdx.x + k * T >= np) break;
-                const double* a = tile + ld * pi[k];
-                const double* b = tile + ld * pj[k];
-                double s = acc[k];
-                for (int r = 0; r < nr; r++) s = fma(a[r], b[r], s);
-                acc[k] = s;
-            }
+            accumulate(gw.tile + (size_t)(c & 1) * gw.tileCap, min(rows, M - c * rows), 1, ld);
             __syncthreads();
         }
     }
     const int ldg = n | 1;
 #pragma unroll
-    for (int k = 0; k < PairsPerThread<T, NM>::value; k++) {
-        if (threadIdx.x + k * T >= np) break;
-        G[pi[k] + ldg * pj[k]] = acc[k];
-        G[pj[k] + ldg * pi[k]] = acc[k];
+    for (int k = 0; k < GPT; k++) {
+#pragma unroll
+        for (int u = 0; u < kGB; u++) {
+            if (u >= gc[k]) continue;
+            G[(gi[k] + u) + ldg * gj[k]] = acc[k][u];
+            G[gj[k] + ldg * (gi[k] + u)] = acc[k][u];
+        }
     }
     __syncthreads();
 }
@@ -634,7 +640,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
     const int matElems = (nmaxS | 1) * nmaxS;
     __shared__ double sDv[3 * kMaxN], sEv[3 * kMaxN];
     __shared__ int sOrder[3 * kMaxN];
-    __shared__ unsigned short sPairs[kMaxN * (kMaxN + 1) / 2];
+    __shared__ unsigned short sGroups[gram_groups(kMaxN)];
     __shared__ int sR[3];
     __shared__ double sRed[T / 32][5];
     __shared__ TetRec rec;
@@ -646,8 +652,8 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
     w.rsel = sR;
     w.gw.tile = sDyn + (size_t)3 * matElems;
     w.gw.tileCap = max(nmaxS | 1, (nmaxS + kQB - 1) / kQB * kQB) * nmaxS;   // also stages a padded factor (mode_apply)
-    w.gw.pairs = sPairs;
-    build_pairs(sPairs, nmaxS);
+    w.gw.groups = sGroups;
+    build_groups(sGroups, nmaxS);
     __shared__ long long sProf[8];
     if (threadIdx.x < 8) sProf[threadIdx.x] = 0;
     w.prof = (P.prof && blockIdx.x == 0 && threadIdx.x == 0) ? sProf : nullptr;
