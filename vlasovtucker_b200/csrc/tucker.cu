@@ -115,35 +115,39 @@ __device__ void mode_apply(const double* __restrict__ src, double* __restrict__ 
 }
 
 // ---- Gram matrices of the three unfoldings, G_k = X_(k) X_(k)^T, accumulated from shared-memory
-// tiles.  The (i <= j) entries of a column j are cut into groups of kGB consecutive i; a thread owns
-// a fixed set of groups (table in shared memory) and keeps their sums in registers across tiles:
-// one operand b_j feeds kGB FMAs, 1.25 shared loads per FMA instead of 2.  G is written symmetric
+// tiles.  A group is one row i against a block of kGB consecutive columns j0..j0+kGB-1 (entries with
+// j < i are computed and dropped); a thread owns a fixed set of groups (table in shared memory) and
+// keeps their sums in registers across tiles: one operand a_i feeds kGB FMAs, 1.25 shared loads per
+// FMA instead of 2.  Consecutive threads take consecutive rows of the same column block, so the a_i
+// loads of a warp are consecutive words and the b_j loads are broadcasts.  G is written symmetric
 // with leading dimension ld = n | 1 (odd, so that both row and column walks are bank-conflict free
 // in the eigen-solver).
 constexpr int kGB = 4;
-// number of groups of an n x n Gram matrix: sum_j ceil((j + 1) / kGB)
-__host__ __device__ constexpr int gram_groups(int n)
+// number of table entries that cover an n x n Gram matrix when the table was laid out for nmax:
+// column block jb holds the rows 0 .. min(kGB*jb + kGB, nmax) - 1
+__host__ __device__ constexpr int gram_groups(int n, int nmax)
 {
     int g = 0;
-    for (int j = 0; j < n; j++) g += (j + kGB) / kGB;
+    for (int jb = 0; jb * kGB < n; jb++) g += (kGB * jb + kGB < nmax) ? kGB * jb + kGB : nmax;
     return g;
 }
 // groups per thread for a kernel instance serving grids of up to NM nodes per axis with T threads
-template <int T, int NM> struct GroupsPerThread { static constexpr int value = (gram_groups(NM) + T - 1) / T; };
+template <int T, int NM> struct GroupsPerThread { static constexpr int value = (gram_groups(NM, NM) + T - 1) / T; };
 
 struct GramWork {
     double* tile;              // two buffers of tileCap doubles each
     int tileCap;
-    const unsigned short* groups;   // group q -> i0 | (j << 8); enumerated column by column, so the
-                                    // first gram_groups(n) entries are the groups of any n <= nmax
+    const unsigned short* groups;   // group q -> i | (j0 << 8); enumerated block by block, rows
+                                    // consecutive; laid out for nmax (rows >= n of a smaller matrix are skipped)
+    int nmax;
 };
 
 __device__ void build_groups(unsigned short* groups, int nmax)
 {
-    for (int j = threadIdx.x; j < nmax; j += blockDim.x) {
-        int base = 0;
-        for (int c = 0; c < j; c++) base += (c + kGB) / kGB;
-        for (int i0 = 0; i0 <= j; i0 += kGB) groups[base + i0 / kGB] = (unsigned short)(i0 | (j << 8));
+    for (int jb = threadIdx.x; jb * kGB < nmax; jb += blockDim.x) {
+        const int base = gram_groups(jb * kGB, nmax);
+        const int rows = min(kGB * jb + kGB, nmax);
+        for (int i = 0; i < rows; i++) groups[base + i] = (unsigned short)(i | ((jb * kGB) << 8));
     }
     __syncthreads();
 }
@@ -167,9 +171,9 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
 {
     constexpr int GPT = GroupsPerThread<T, NM>::value;
     const int n = d[mode];
-    const int ng = gram_groups(n);
+    const int ng = gram_groups(n, gw.nmax);
     double acc[GPT][kGB];
-    int gi[GPT], gj[GPT], gc[GPT];   // first row, column, rows in the group (0: no group)
+    int gi[GPT], gj[GPT], gc[GPT];   // row, first column, columns in the group (0: no group)
 #pragma unroll
     for (int k = 0; k < GPT; k++) {
 #pragma unroll
@@ -178,7 +182,7 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
         const unsigned short e = q < ng ? gw.groups[q] : 0;
         gi[k] = e & 255;
         gj[k] = e >> 8;
-        gc[k] = q < ng ? min(kGB, gj[k] + 1 - gi[k]) : 0;
+        gc[k] = (q < ng && gi[k] < n) ? min(kGB, n - gj[k]) : 0;
     }
     const int n0 = d[0], n1 = d[1], n2 = d[2], M = n0 * n1;
     // accumulate one tile: element (row r of operand i) sits at tile[aStep * r + aOff(i)]
@@ -186,14 +190,14 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
 #pragma unroll
         for (int k = 0; k < GPT; k++) {
             if (gc[k] == 0) continue;
-            const double* b = tile + colStride * gj[k];
-            int off[kGB];   // rows past the end of a short group repeat its last row (their sums are dropped)
+            const double* a = tile + colStride * gi[k];
+            int off[kGB];   // columns past the end of a short block repeat its last column (their sums are dropped)
 #pragma unroll
-            for (int u = 0; u < kGB; u++) off[u] = colStride * (gi[k] + min(u, gc[k] - 1));
+            for (int u = 0; u < kGB; u++) off[u] = colStride * (gj[k] + min(u, gc[k] - 1));
             for (int r = 0; r < len; r++) {
-                const double bv = b[rowStride * r];
+                const double av = a[rowStride * r];
 #pragma unroll
-                for (int u = 0; u < kGB; u++) acc[k][u] = fma(tile[rowStride * r + off[u]], bv, acc[k][u]);
+                for (int u = 0; u < kGB; u++) acc[k][u] = fma(av, tile[rowStride * r + off[u]], acc[k][u]);
             }
         }
     };
@@ -253,9 +257,9 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
     for (int k = 0; k < GPT; k++) {
 #pragma unroll
         for (int u = 0; u < kGB; u++) {
-            if (u >= gc[k]) continue;
-            G[(gi[k] + u) + ldg * gj[k]] = acc[k][u];
-            G[gj[k] + ldg * (gi[k] + u)] = acc[k][u];
+            if (u >= gc[k] || gj[k] + u < gi[k]) continue;   // upper triangle (j >= i) only
+            G[gi[k] + ldg * (gj[k] + u)] = acc[k][u];
+            G[(gj[k] + u) + ldg * gi[k]] = acc[k][u];
         }
     }
     __syncthreads();
@@ -640,7 +644,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
     const int matElems = (nmaxS | 1) * nmaxS;
     __shared__ double sDv[3 * kMaxN], sEv[3 * kMaxN];
     __shared__ int sOrder[3 * kMaxN];
-    __shared__ unsigned short sGroups[gram_groups(kMaxN)];
+    __shared__ unsigned short sGroups[gram_groups(kMaxN, kMaxN)];
     __shared__ int sR[3];
     __shared__ double sRed[T / 32][5];
     __shared__ TetRec rec;
@@ -653,6 +657,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
     w.gw.tile = sDyn + (size_t)3 * matElems;
     w.gw.tileCap = max(nmaxS | 1, (nmaxS + kQB - 1) / kQB * kQB) * nmaxS;   // also stages a padded factor (mode_apply)
     w.gw.groups = sGroups;
+    w.gw.nmax = nmaxS;
     build_groups(sGroups, nmaxS);
     __shared__ long long sProf[8];
     if (threadIdx.x < 8) sProf[threadIdx.x] = 0;
