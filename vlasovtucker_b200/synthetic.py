@@ -144,3 +144,20 @@ def periodic_kuhn_tables(nx, ny, nz, lengths=(1.0, 1.0, 1.0), brick=None):
     if brick is not None:
         mt.order, mt.brickTets = brick_order(nx, ny, nz, brick)
     return mt
+
+
+def write_msh(path, nodes, tets, tris, tri_entity):
+    """MSH 2.2 ASCII file as SURVEY.md §8d specifies the C4 input: node tags 1..n in order, boundary
+    triangles first (the owning tet's outward vertex order, elementary tags = entities), then all
+    tetrahedra in one volume entity.  This is the file the reference's ``Mesh(std::string)`` reads."""
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(nodes))
+        np.savetxt(f, np.column_stack([np.arange(1, len(nodes) + 1), nodes]), fmt="%d %.17g %.17g %.17g")
+        f.write("$EndNodes\n$Elements\n%d\n" % (len(tris) + len(tets)))
+        nt = len(tris)
+        ids = np.arange(1, nt + 1)
+        np.savetxt(f, np.column_stack([ids, np.full(nt, 2), np.full(nt, 2), tri_entity, tri_entity, tris + 1]), fmt="%d")
+        ids = np.arange(nt + 1, nt + len(tets) + 1)
+        one = np.ones(len(tets), np.int64)
+        np.savetxt(f, np.column_stack([ids, 4 * one, 2 * one, one, one, tets + 1]), fmt="%d")
+        f.write("$EndElements\n")
