@@ -18,37 +18,39 @@ struct MeshContext;
 
 class Full {
 public:
-    Full() {}
-    Full(const Tensor3d& tensor);
-    Full(const Full& other);                 // copies materialise: the copy is a host value
-    Full(Full&& other) noexcept;             // moves keep the binding (std::vector growth)
-    Full& operator=(const Full& other);      // into a handle: uploads the row
-    Full& operator=(Full&& other) noexcept;
-
-    int Size() const;
-    std::array<int, 3> Dimensions() const;
-    double operator()(int i0, int i1, int i2) const;
-    Tensor3d Reconstructed() const;
-    double Sum() const;
-    Full& Compress(double precision = 0, int maxRank = 1e+6);   // no-op, as the reference
-
-    friend std::ostream& operator<<(std::ostream& out, const Full& t);
-
-    Full& operator+=(const Full& t);
-    Full& operator-=(const Full& t);
-    Full& operator*=(const Full& t);
-    Full& operator*=(double d);
-
-    friend Full operator+(const Full& t1, const Full& t2);
-    friend Full operator-(const Full& t1, const Full& t2);
-    friend Full operator*(const Full& t1, const Full& t2);
-    friend Full operator*(double d, const Full& t);
-    friend Full operator*(const Full& t, double d);
-    friend Full operator-(const Full& t);
-
     // ---- device binding (not part of the reference API)
     static Full DeviceRow(std::shared_ptr<device::MeshContext> ctx, int species, int tet, std::array<int, 3> dims);
     bool OnDevice() const { return _tet >= 0; }
+
+    // ---- construction / assignment
+    Full() {}
+    Full(const Tensor3d& tensor);
+    Full(Full&& other) noexcept;             // moves keep the binding (std::vector growth)
+    Full(const Full& other);                 // copies materialise: the copy is a host value
+    Full& operator=(Full&& other) noexcept;
+    Full& operator=(const Full& other);      // into a handle: uploads the row
+
+    // ---- element-wise algebra (same operator set as Tucker, so Solver<T> code is format agnostic)
+    friend Full operator-(const Full& t);
+    friend Full operator*(double d, const Full& t);
+    friend Full operator*(const Full& t, double d);
+    friend Full operator*(const Full& t1, const Full& t2);
+    friend Full operator-(const Full& t1, const Full& t2);
+    friend Full operator+(const Full& t1, const Full& t2);
+    Full& operator*=(double d);
+    Full& operator*=(const Full& t);
+    Full& operator-=(const Full& t);
+    Full& operator+=(const Full& t);
+    Full& Compress(double precision = 0, int maxRank = 1e+6);   // no-op, as the reference
+
+    // ---- queries
+    double operator()(int i0, int i1, int i2) const;
+    Tensor3d Reconstructed() const;
+    double Sum() const;
+    std::array<int, 3> Dimensions() const;
+    int Size() const;
+
+    friend std::ostream& operator<<(std::ostream& out, const Full& t);
 
 private:
     Tensor3d Value() const;   // host value, fetched from the device for handles

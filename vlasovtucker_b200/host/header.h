@@ -1,17 +1,17 @@
-// Umbrella include of the public API (reference: src/header.h:1-14).
+// Everything a driver needs (reference: src/header.h): the drivers in examples/ and test/ include
+// only this file.
 #pragma once
+#include "log.h"
+#include "timer.h"
 #include "typedefs.h"
-
-#include "mesh.h"
-#include "particle_data.h"
-#include "velocity_grid.h"
+#include "vtk.h"
 
 #include "full.h"
 #include "tucker.h"
 
-#include "multicomponent_solver.h"
-#include "solver.h"
+#include "mesh.h"
+#include "velocity_grid.h"
+#include "particle_data.h"
 
-#include "log.h"
-#include "timer.h"
-#include "vtk.h"
+#include "solver.h"
+#include "multicomponent_solver.h"

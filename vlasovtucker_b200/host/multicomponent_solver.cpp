@@ -11,7 +11,7 @@
 namespace VlasovTucker {
 
 template <typename T>
-MulticomponentSolver<T>::MulticomponentSolver(Solver<T>* base) : _solvers({base})
+MulticomponentSolver<T>::MulticomponentSolver(Solver<T>* base) : _log(LogLevel::Console), _solvers({base})
 {
     _log = Log(LogLevel::Console);
 }

@@ -1,5 +1,6 @@
-// Multi-species loop with one shared Poisson solve and per-species sub-cycling
-// (reference: src/multicomponent_solver.h:7-30).
+// Several species advanced together: one shared Poisson solve per iteration, each species stepped
+// by its own Solver with its own sub-cycling multiplier (the public type of
+// src/multicomponent_solver.h:7-30; the loop itself is multicomponent_solver.cpp:27-135).
 #pragma once
 #include <limits.h>
 
@@ -11,19 +12,24 @@
 namespace VlasovTucker {
 template <typename TensorType>
 class MulticomponentSolver {
+    using SolverPtr = Solver<TensorType>*;
+
 public:
-    MulticomponentSolver(Solver<TensorType>* baseSolver);
-    void AddSolver(Solver<TensorType>* solver);
+    // run parameters (public data, assigned by the driver before Solve)
+    int nIterations = 0;
+    double timeStep = 0;
+    int writeStep = INT_MAX;
+    // species s updates when iteration % stepMultipliers[s] == 0, with dt * multiplier;
+    // keyed by solver address as the drivers do (examples/sheath.cpp:131-132)
+    std::map<SolverPtr, int> stepMultipliers;
+
+    // baseSolver owns the field solve (its PoissonSolver and field BCs are the ones used)
+    MulticomponentSolver(SolverPtr baseSolver);
+    void AddSolver(SolverPtr solver);
     void Solve();
 
-public:
-    double timeStep = 0;
-    std::map<Solver<TensorType>*, int> stepMultipliers;   // update a species once in several steps
-    int nIterations = 0;
-    int writeStep = INT_MAX;
-
 private:
-    std::vector<Solver<TensorType>*> _solvers;
     Log _log;
+    std::vector<SolverPtr> _solvers;   // baseSolver first
 };
 }  // namespace VlasovTucker

@@ -18,6 +18,7 @@ namespace device {
 struct MeshContext;
 }
 
+// Parameters of SetMaxwellPDF: density per tet, temperature (0 = all particles at mostProbableV)
 struct MaxwellPDF {
     std::vector<double> physDensity;
     double temperature;
@@ -27,40 +28,44 @@ struct MaxwellPDF {
 template <typename TensorType>
 class ParticleData {
 public:
+    // public data, as the drivers use it
+    std::string species = "";
+    double mass;
+    double charge;
+    std::vector<TensorType> pdf;   // one entry per tet
+
     ParticleData(const Mesh* mesh, const VelocityGrid* vGrid);
 
+    // initial condition: Maxwellian normalised discretely to physDensity (particle_data.cpp:23-90)
     void SetMaxwellPDF(const MaxwellPDF& paramsPDF);
 
+    // moments: sum_v f * cellVolume and sum_v v f * cellVolume / density (device reductions)
     std::vector<double> Density() const;
     std::vector<Vector3d> Velocity() const;
 
+    // Tucker rounding parameters (ignored by Full)
     void SetCompressionError(double error);
     double CompressionError() const;
     int MaxRank() const;
     void SetMaxRank(int maxRank);   // addition: fixed-rank configurations
 
-    // device binding (not in the reference API)
+    // ---- device binding (not in the reference API)
     std::shared_ptr<device::MeshContext> DeviceContext() const { return _dev; }
     int DeviceSpecies() const { return _species; }
     void PushParams() const;        // mass/charge are public members assigned after construction
     void SyncFromDevice();          // Tucker: refresh the host mirror `pdf` from the device state
 
-public:
-    std::string species = "";
-    double mass;
-    double charge;
-    std::vector<TensorType> pdf;
-
 private:
     const Mesh* _mesh;
     const VelocityGrid* _vGrid;
-    double _comprErr = 1e-10;
-    int _maxRank;
     std::shared_ptr<device::MeshContext> _dev;
     int _species = -1;
+    int _maxRank;
+    double _comprErr = 1e-10;
 };
 
-std::vector<double> ScalarField(const Mesh* mesh, std::function<double(const Point&)> densityFunc);
+// helpers of the drivers (particle_data.cpp:145-162)
 double DebyeLength(double temperature, double density, double charge);
 double PlasmaFrequency(double density, double charge, double mass);
+std::vector<double> ScalarField(const Mesh* mesh, std::function<double(const Point&)> densityFunc);
 }  // namespace VlasovTucker

@@ -11,37 +11,40 @@
 
 namespace VlasovTucker {
 class Tucker {
+    using Factors = std::array<Eigen::MatrixXd, 3>;
+
 public:
+    // ---- construction
     Tucker();
-    Tucker(int n0, int n1, int n2, int r0, int r1, int r2);                        // zero tensor of given ranks
-    Tucker(const Tensor3d& tensor, double precision = 0, int maxRank = 1e+6);     // truncated HOSVD
-    Tucker(const Tensor3d& core, const std::array<Eigen::MatrixXd, 3>& u);
+    Tucker(const Tensor3d& core, const Factors& u);                             // from parts
+    Tucker(const Tensor3d& tensor, double precision = 0, int maxRank = 1e+6);   // truncated HOSVD
+    Tucker(int n0, int n1, int n2, int r0, int r1, int r2);                      // zero tensor of given ranks
 
-    Tucker& Compress(double precision = 0, int maxRank = 1e+6);
-    Tensor3d Reconstructed() const;
-
-    int Size() const;
-    std::array<int, 3> Dimensions() const;
-    std::array<int, 3> Ranks() const;
-    std::array<Eigen::MatrixXd, 3> U() const;
-    Tensor3d Core() const;
-
-    double Sum() const;
-    double Norm() const;
-
-    double operator()(int i0, int i1, int i2) const;
-
-    Tucker& operator+=(const Tucker& t);
-    Tucker& operator-=(const Tucker& t);
-    Tucker& operator*=(const Tucker& t);
-    Tucker& operator*=(double d);
-
-    friend Tucker operator+(const Tucker& t1, const Tucker& t2);
-    friend Tucker operator-(const Tucker& t1, const Tucker& t2);
-    friend Tucker operator*(const Tucker& t1, const Tucker& t2);   // Hadamard product
+    // ---- element-wise algebra; ranks add under +/-, multiply under * (Hadamard), scalars touch the core
+    friend Tucker operator-(const Tucker& t);
     friend Tucker operator*(double d, const Tucker& t);
     friend Tucker operator*(const Tucker& t, double d);
-    friend Tucker operator-(const Tucker& t);
+    friend Tucker operator*(const Tucker& t1, const Tucker& t2);
+    friend Tucker operator-(const Tucker& t1, const Tucker& t2);
+    friend Tucker operator+(const Tucker& t1, const Tucker& t2);
+    Tucker& operator*=(double d);
+    Tucker& operator*=(const Tucker& t);
+    Tucker& operator-=(const Tucker& t);
+    Tucker& operator+=(const Tucker& t);
+
+    // ---- rounding: QR of the factors, HOSVD of the transformed core, keep sigma_j > precision*|sigma|/sqrt(3)
+    Tucker& Compress(double precision = 0, int maxRank = 1e+6);
+
+    // ---- queries
+    double operator()(int i0, int i1, int i2) const;
+    Tensor3d Reconstructed() const;
+    double Sum() const;
+    double Norm() const;
+    Tensor3d Core() const;
+    Factors U() const;
+    std::array<int, 3> Ranks() const;
+    std::array<int, 3> Dimensions() const;
+    int Size() const;   // doubles stored: core + factors
 
     friend std::ostream& operator<<(std::ostream& out, const Tucker& t);
 
@@ -50,7 +53,7 @@ private:
 
     std::array<int, 3> _n;
     std::array<int, 3> _r;
-    std::array<Eigen::MatrixXd, 3> _u;
+    Factors _u;
     Tensor3d _core;
 };
 

@@ -2,7 +2,7 @@
 
 namespace VlasovTucker {
 
-VelocityGrid::VelocityGrid(std::array<int, 3> n, Vector3d lo, Vector3d hi) : nCells(n), maxV(hi), minV(lo)
+VelocityGrid::VelocityGrid(std::array<int, 3> n, Vector3d lo, Vector3d hi) : nCells(n), minV(lo), maxV(hi)
 {
     nCellsTotal = n[0] * n[1] * n[2];
     for (int j = 0; j < 3; j++) step[j] = (maxV[j] - minV[j]) / (nCells[j] - 1);   // nodes, not cells
