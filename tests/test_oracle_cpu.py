@@ -185,3 +185,24 @@ def test_sheath_constants(oracle_mod):
     wp = e * np.sqrt(1e17 / (me * EPS0))
     assert abs(debye - 2.3529069315788665e-05) < 1e-19
     assert abs(wp - 1.782902734810009e10) < 1e-3
+
+
+def test_poisson_known_answer_periodic_box(oracle_mod):
+    """test/poisson_test.cpp:122-208 (Test 2): fully periodic box, pinned row 0 (no Dirichlet BC).
+    SURVEY.md §8c: nnz 24,771, RMS phi error 1.04 (the pinned row offsets phi by -phi_A(tet 0) and the
+    mesh has ~3.5 cells per wavelength), RMS E error 2.87 with |E|_rms ~ 10.9."""
+    m = oracle_mod.Mesh.load(mesh_path("box_4955_tets.msh"), [(1, 2), (3, 4), (5, 6)])
+    p = oracle_mod.Poisson(m)
+    p.initialize()
+    c = m.tetCentroid
+    arg = 2 * PI * (c[:, 0] + c[:, 1] + 2 * c[:, 2])
+    rho = EPS0 * 4 * PI * PI * 6 * np.sin(arg)
+    for _ in range(5):
+        phi, E = p.solve(rho)
+    assert len(p.csr()[2]) == 24771
+    assert phi[0] == 0.0                                   # pinned (poisson.cpp:128-134, 248-254)
+    phiA = np.sin(arg)
+    EA = np.stack([-2 * PI * np.cos(arg), -2 * PI * np.cos(arg), -4 * PI * np.cos(arg)], 1)
+    assert abs(np.sqrt(((phi - phiA) ** 2).mean()) - 1.04) < 0.01
+    assert abs(np.sqrt(((E - EA) ** 2).sum(1).mean()) - 2.87) < 0.01
+    assert abs(np.sqrt((EA ** 2).sum(1).mean()) - 10.9) < 0.1
