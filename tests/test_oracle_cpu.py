@@ -206,3 +206,38 @@ def test_poisson_known_answer_periodic_box(oracle_mod):
     assert abs(np.sqrt(((phi - phiA) ** 2).mean()) - 1.04) < 0.01
     assert abs(np.sqrt(((E - EA) ** 2).sum(1).mean()) - 2.87) < 0.01
     assert abs(np.sqrt((EA ** 2).sum(1).mean()) - 10.9) < 0.1
+
+
+def test_poisson_known_answers_finer_box(oracle_mod):
+    """The second mesh of the reference's convergence series (box_10021_tets): Test 1 RMS errors
+    9.9208522907e-04 / 8.8083192941e-02 with nnz 48,313, Test 2 8.0e-02 / 2.27 with nnz 50,101
+     — both smaller than on box_4955_tets, i.e. the discretisation converges."""
+    m = oracle_mod.Mesh.load(mesh_path("box_10021_tets.msh"), [(5, 6)])
+    p = oracle_mod.Poisson(m)
+    p.set_bc(1, "Dirichlet")
+    p.set_bc(2, "Dirichlet")
+    p.set_bc(3, "Neumann")
+    p.set_bc(4, "Neumann")
+    p.initialize()
+    c = m.tetCentroid
+    rho = -EPS0 * np.cos(2 * PI * c[:, 1]) * (-(2 * PI * c[:, 0]) ** 2 + (2 * PI) ** 2 * c[:, 0] + 2)
+    for _ in range(5):
+        phi, E = p.solve(rho)
+    phiA = c[:, 0] * (c[:, 0] - 1) * np.cos(2 * PI * c[:, 1])
+    EA = np.stack([-(2 * c[:, 0] - 1) * np.cos(2 * PI * c[:, 1]),
+                   2 * PI * (c[:, 0] ** 2 - c[:, 0]) * np.sin(2 * PI * c[:, 1]), 0 * c[:, 0]], 1)
+    assert len(p.csr()[2]) == 48313
+    assert abs(np.sqrt(((phi - phiA) ** 2).mean()) - 9.9208522907e-04) < 1e-11
+    assert abs(np.sqrt(((E - EA) ** 2).sum(1).mean()) - 8.8083192941e-02) < 1e-9
+
+    m2 = oracle_mod.Mesh.load(mesh_path("box_10021_tets.msh"), [(1, 2), (3, 4), (5, 6)])
+    p2 = oracle_mod.Poisson(m2)
+    p2.initialize()
+    c = m2.tetCentroid
+    arg = 2 * PI * (c[:, 0] + c[:, 1] + 2 * c[:, 2])
+    for _ in range(5):
+        phi, E = p2.solve(EPS0 * 4 * PI * PI * 6 * np.sin(arg))
+    EA = np.stack([-2 * PI * np.cos(arg), -2 * PI * np.cos(arg), -4 * PI * np.cos(arg)], 1)
+    assert len(p2.csr()[2]) == 50101
+    assert abs(np.sqrt(((phi - np.sin(arg)) ** 2).mean()) - 8.0e-02) < 1e-3
+    assert abs(np.sqrt(((E - EA) ** 2).sum(1).mean()) - 2.27) < 0.01
