@@ -162,6 +162,13 @@ def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fus
                        f"OpenMP {threads} threads)", ms_per_step=dt * 1e3)
 
 
+def workload_name(hexes, nv):
+    """The workload both arms report (config.workload)."""
+    nT = 6 * hexes[0] * hexes[1] * hexes[2]
+    return (f"C4 per-GPU share: periodic Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]} hexes x6 = {nT} tets/GPU "
+            f"x {nv}^3 velocity nodes, full format, electrons (Maxwellian 1 eV, 1% density wave), dt=1e-3 T_p")
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -172,7 +179,8 @@ def run_reference(args):
         "unit": "updates/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 1)),
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4 per-GPU share (Kuhn 28^3x6 tets x 32^3 v-nodes, full format); CPU arm timed on a bounded sample",
+        "config": {"workload": workload_name(tuple(args.hexes), args.nv),
+                   "cpu_arm": "timed on a bounded sample of the workload (see cpu_baseline.sample)",
                    "note": "reference itself cannot be compiled here (vendored Eigen lacks Eigen/Core); this is the oracle's line-by-line restatement"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -315,8 +323,7 @@ def run_gpu(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"C4 per-GPU share: periodic Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]} hexes x6 = {nT} tets/GPU "
-                            f"x {nv}^3 velocity nodes, full format, electrons (Maxwellian 1 eV, 1% density wave), dt=1e-3 T_p",
+                "workload": workload_name(hexes, nv),
                 "tets_per_gpu": nT, "v_nodes": N, "state_bytes_per_gpu": 2 * nT * N * 8,
                 "l2_policy": "inputs larger than L2 (state is %.1f GB per copy); no flush needed" % (nT * N * 8 / 1e9),
                 "brick_hexes": list(args.brick), "chunk_planes": args.chunk_planes, "kernel_variant": args.variant,
