@@ -81,3 +81,16 @@ def test_brick_order_is_a_permutation_of_compact_bricks():
     assert mt.brickTets == 6 * 27
     c = mt.tetCentroid[mt.order[:mt.brickTets]]
     assert (c.max(0) - c.min(0)).max() < 0.5 + 1e-12     # first brick spans 3 of 6 cells per axis
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header compiles as C99 and as C++ without any CUDA or
+    torch type in a signature."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "vt_b200.h")
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+        r = subprocess.run(["/usr/bin/gcc", "-x", lang, std, "-Wall", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)      # declarations only, comments stripped
+    for banned in ("cuda", "torch", "at::", "std::", "Tensor"):
+        assert banned not in code, banned
