@@ -33,7 +33,49 @@ int main(int argc, char** argv)
     const string which = argv[1], meshFile = argv[2], outFile = argv[4];
     const int iterations = atoi(argv[3]);
     ofstream out(outFile, ios::binary);
-    if (which == "oscillations_tucker") {
+    if (which == "snapshot" || which == "snapshot_tucker") {
+        // WriteSnapshot / ReadSnapshot round trip: run a few iterations, write, read into a second
+        // ParticleData on the same mesh; both states are dumped
+        Mesh mesh(meshFile);
+        mesh.SetPeriodicBounaries({{1, 2}, {3, 4}, {5, 6}});
+        mesh.Reconstruct();
+        VelocityGrid vGrid({11, 9, 7}, {-3, -1, -1}, {3, 1, 1});
+        double L = 0;
+        for (auto* p : mesh.points) L = max(L, (*p)[0]);
+        MaxwellPDF paramsPDF;
+        paramsPDF.physDensity = ScalarField(&mesh, [L](const Point& p) { return 10 + 0.2 * sin(p[0] / L * (2 * pi)); });
+        paramsPDF.temperature = 0.3 / boltzConst;
+        paramsPDF.mostProbableV = {0.4, 0, 0};
+        const string snap = outFile + ".snap";
+        auto run = [&](auto& first, auto& second, auto& solver) {
+            first.species = "custom";
+            first.mass = 1;
+            first.charge = 2.975e-5;
+            first.SetCompressionError(1e-6);
+            first.SetMaxwellPDF(paramsPDF);
+            solver.backgroundChargeDensity = vector<double>(mesh.tets.size(), -first.charge * 10);
+            solver.timeStep = 1e-3;
+            solver.nIterations = iterations;
+            solver.Solve();
+            first.WriteSnapshot(snap);
+            second.mass = first.mass;
+            second.charge = first.charge;
+            second.SetCompressionError(1e-6);
+            second.ReadSnapshot(snap);
+            DumpState(out, mesh, first);
+            DumpState(out, mesh, second);
+        };
+        if (which == "snapshot") {
+            ParticleData<Full> a(&mesh, &vGrid), b(&mesh, &vGrid);
+            Solver<Full> solver(&mesh, &vGrid, &a);
+            run(a, b, solver);
+        } else {
+            ParticleData<Tucker> a(&mesh, &vGrid), b(&mesh, &vGrid);
+            Solver<Tucker> solver(&mesh, &vGrid, &a);
+            run(a, b, solver);
+        }
+        remove(snap.c_str());
+    } else if (which == "oscillations_tucker") {
         // the same driver with TensorType = Tucker (examples/oscillations.cpp switches by one typedef);
         // a warm drifting Maxwellian so that the ranks are not trivially 1
         Mesh mesh(meshFile);

@@ -3,6 +3,10 @@
 #include <algorithm>
 #include <cmath>
 #include <iostream>
+#include <stdexcept>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
 #include <type_traits>
 
 #include "device.h"
@@ -29,15 +33,21 @@ void ParticleData<T>::PushParams() const
 }
 
 template <>
+void ParticleData<Full>::RebindRows()
+{
+    pdf.clear();
+    pdf.reserve(_mesh->tets.size());
+    for (size_t t = 0; t < _mesh->tets.size(); t++)
+        pdf.push_back(Full::DeviceRow(_dev, _species, (int)t, _vGrid->nCells));
+}
+
+template <>
 void ParticleData<Full>::SetMaxwellPDF(const MaxwellPDF& params)
 {
     PushParams();   // the Maxwellian uses `mass`
     device::Check(vt_species_set_maxwell(_dev->ctx, _species, params.physDensity.data(), params.temperature,
                                          params.mostProbableV.data()));
-    pdf.clear();
-    pdf.reserve(_mesh->tets.size());
-    for (size_t t = 0; t < _mesh->tets.size(); t++)
-        pdf.push_back(Full::DeviceRow(_dev, _species, (int)t, _vGrid->nCells));
+    RebindRows();
     std::cout << "PDF size reduction: " << 1.0 << " times on average\n";
 }
 
@@ -62,6 +72,11 @@ void ParticleData<Tucker>::SyncFromDevice()
 }
 template <>
 void ParticleData<Full>::SyncFromDevice() {}
+template <>
+void ParticleData<Tucker>::RebindRows()
+{
+    SyncFromDevice();
+}
 
 template <>
 void ParticleData<Tucker>::SetMaxwellPDF(const MaxwellPDF& params)
@@ -108,6 +123,59 @@ void ParticleData<T>::SetMaxRank(int r)
 {
     _maxRank = r;
     if (std::is_same<T, Tucker>::value) device::Check(vt_tucker_enable(_dev->ctx, _species, _comprErr, _maxRank));
+}
+
+namespace {
+struct SnapshotHeader {
+    char magic[8];
+    int32_t nTets, n[3], format;
+};
+const char kSnapMagic[8] = {'V', 'T', 'S', 'N', 'A', 'P', '1', 0};
+}  // namespace
+
+template <typename T>
+void ParticleData<T>::WriteSnapshot(const std::string& path) const
+{
+    std::ofstream out(path, std::ios::binary);
+    if (!out) throw std::runtime_error("Cannot open snapshot file for writing: " + path);
+    SnapshotHeader h;
+    std::memcpy(h.magic, kSnapMagic, 8);
+    h.nTets = (int32_t)_mesh->tets.size();
+    for (int k = 0; k < 3; k++) h.n[k] = _vGrid->nCells[k];
+    h.format = std::is_same<T, Tucker>::value ? 1 : 0;
+    out.write((const char*)&h, sizeof(h));
+    const size_t N = (size_t)_vGrid->nCellsTotal;
+    const int batch = (int)std::max<size_t>(1, (64u << 20) / (N * sizeof(double)));
+    std::vector<double> buf((size_t)batch * N);
+    for (int first = 0; first < h.nTets; first += batch) {
+        const int count = std::min(batch, h.nTets - first);
+        device::Check(vt_species_get_pdf(_dev->ctx, _species, first, count, buf.data()));
+        out.write((const char*)buf.data(), (std::streamsize)((size_t)count * N * sizeof(double)));
+    }
+    if (!out) throw std::runtime_error("Error while writing snapshot: " + path);
+}
+
+template <typename T>
+void ParticleData<T>::ReadSnapshot(const std::string& path)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw std::runtime_error("Cannot open snapshot file: " + path);
+    SnapshotHeader h;
+    in.read((char*)&h, sizeof(h));
+    if (!in || std::memcmp(h.magic, kSnapMagic, 8) != 0) throw std::runtime_error("Not a snapshot file: " + path);
+    if (h.nTets != (int32_t)_mesh->tets.size() || h.n[0] != _vGrid->nCells[0] || h.n[1] != _vGrid->nCells[1] ||
+        h.n[2] != _vGrid->nCells[2])
+        throw std::invalid_argument("Snapshot does not match the mesh or the velocity grid");
+    const size_t N = (size_t)_vGrid->nCellsTotal;
+    const int batch = (int)std::max<size_t>(1, (64u << 20) / (N * sizeof(double)));
+    std::vector<double> buf((size_t)batch * N);
+    for (int first = 0; first < h.nTets; first += batch) {
+        const int count = std::min(batch, h.nTets - first);
+        in.read((char*)buf.data(), (std::streamsize)((size_t)count * N * sizeof(double)));
+        if (!in) throw std::runtime_error("Snapshot file is truncated: " + path);
+        device::Check(vt_species_set_pdf(_dev->ctx, _species, first, count, buf.data()));
+    }
+    RebindRows();   // row handles (Full) / host mirror (Tucker), as SetMaxwellPDF leaves them
 }
 
 template class ParticleData<Full>;

@@ -55,7 +55,15 @@ public:
     void PushParams() const;        // mass/charge are public members assigned after construction
     void SyncFromDevice();          // Tucker: refresh the host mirror `pdf` from the device state
 
+    // ---- lossless binary snapshot of the distribution function (addition): every
+    // tet's tensor as doubles in the reference's tet order.  Full: restores the state bit for bit.
+    // Tucker: stores the reconstruction; reading re-rounds it with precision 0.
+    void WriteSnapshot(const std::string& path) const;
+    void ReadSnapshot(const std::string& path);
+
 private:
+    void RebindRows();   // pdf = row handles (Full) or the host mirror of the device state (Tucker)
+
     const Mesh* _mesh;
     const VelocityGrid* _vGrid;
     std::shared_ptr<device::MeshContext> _dev;
