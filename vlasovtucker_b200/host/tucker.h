@@ -57,6 +57,18 @@ private:
     Tensor3d _core;
 };
 
+// Tensor-matrix conversion (tucker.h:76-80): the first rows*cols entries of the tensor's column-major
+// storage seen as a rows x cols matrix.  The reference returns an Eigen::Map onto the tensor; with
+// the stand-in dense types this is a copy.
+template <typename Scalar, int rank, typename sizeType>
+Eigen::MatrixXd TensorToMatrix(const Eigen::Tensor<Scalar, rank>& tensor, const sizeType rows, const sizeType cols)
+{
+    Eigen::MatrixXd m((int)rows, (int)cols);
+    const Scalar* src = tensor.data();
+    for (long i = 0; i < (long)rows * (long)cols; i++) m.data()[i] = (double)src[i];
+    return m;
+}
+
 // Mode-`index` unfolding with the reference's column order (tucker.cpp:337-392): mode 0 columns
 // run i2 fastest then i1; mode 1: i0 fastest then i2; mode 2: i1 fastest then i0.
 Eigen::MatrixXd Unfolding(const Tensor3d& tensor, int index);
