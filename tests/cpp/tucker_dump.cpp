@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <fstream>
 #include <iostream>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "header.h"
@@ -30,6 +32,24 @@ static void Write(std::ofstream& out, const Tucker& t)
 
 int main(int argc, char** argv)
 {
+    if (argc == 2 && std::string(argv[1]) == "errors") {
+        // error behaviour of the algebra (tucker.cpp:193, 262): std::invalid_argument with these texts
+        Tensor3d x(3, 3, 3), y(3, 4, 3);
+        x.setZero();
+        y.setZero();
+        const Tucker tx(x), ty(y);
+        try {
+            (void)(tx + ty);
+        } catch (const std::invalid_argument& e) {
+            std::cout << "sum: " << e.what() << "\n";
+        }
+        try {
+            (void)(tx * ty);
+        } catch (const std::invalid_argument& e) {
+            std::cout << "mult: " << e.what() << "\n";
+        }
+        return 0;
+    }
     if (argc < 8) {
         std::cerr << "usage: tucker_dump in.bin out.bin n0 n1 n2 eps maxRank\n";
         return 2;

@@ -99,6 +99,8 @@ def test_host_tucker_class_matches_oracle(oracle_mod, host_lib, tmp_path):
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", f"-I{HOST}", f"-I{HOST}/standin", "-o", exe,
                            os.path.join(ROOT, "tests", "cpp", "tucker_dump.cpp"), f"-L{ROOT}/vlasovtucker_b200/lib",
                            "-lvlasov_tucker", "-lvt_b200", "-Wl,-rpath," + os.path.join(ROOT, "vlasovtucker_b200", "lib")])
+    out = subprocess.run([exe, "errors"], capture_output=True, text=True, check=True).stdout
+    assert "sum: Different shapes in sum" in out and "mult: Different shapes in mult" in out   # tucker.cpp:193, 262
     n, eps, rmax = (9, 7, 6), 1e-6, 5
     ax = [np.linspace(-1, 1, k) for k in n]
 
