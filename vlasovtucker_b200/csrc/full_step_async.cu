@@ -7,9 +7,10 @@
 // which sustains ~6 TB/s of L2->SM traffic for the 48 B/update this stencil moves through L2 —
 // a third of what the 21-28 TB/s L2 can deliver and too little to saturate HBM.  Registers are
 // the limiter, so here no register holds data in flight: every thread issues 16-byte cp.async
-// (LDGSTS) copies for planes D tickets ahead and computes from shared memory.  (A cp.async.bulk
-// / TMA producer was tried first — full_step_tma.cu — and measured slower: one CTA's bulk copies
-// sustained only ~19 GB/s per SM from HBM.)
+// (LDGSTS) copies for planes D tickets ahead and computes from shared memory.  This kernel is
+// superseded as the default by the warp-specialised cp.async.bulk pipeline of full_step_tma.cu
+// (a dedicated producer thread, mbarrier rings, no block-wide barrier: 18.6 ms against 28.8-36 ms
+// here on the C4 share) and stays as an opt-in variant (vt_step_config bit 3) and a parity case.
 //
 // Structure: one CTA per SM, persistent.  Work items (tet, chunk of i2-planes) are handed out in
 // brick-major order through a global atomic counter, so all SMs stay inside a narrow window of
