@@ -1,17 +1,22 @@
-"""Builds libvt_b200.so (hand-written sm_100a CUDA + the C ABI of include/vt_b200.h) in-tree."""
+"""Builds libvt_b200.so (hand-written sm_100a CUDA + the C ABI of include/vt_b200.h) in-tree.
+
+One nvcc process per translation unit, run concurrently, then one link step: the objects live in
+vlasovtucker_b200/build/obj (git-ignored like the library itself)."""
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build", "obj")
 LIB = os.path.join(LIBDIR, "libvt_b200.so")
 SOURCES = ["vt_api.cu", "full_step.cu", "full_step_async.cu", "full_step_tma.cu", "poisson.cu", "halo.cu", "tucker.cu"]
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--shared", "-cudart", "shared",
-]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
+# the system host compiler; the image exports CXX/CC pointing at a wrapper nvcc cannot use
+HOST_CXX = ["-ccbin", "/usr/bin/g++"]
 
 
 def nvcc():
@@ -21,27 +26,43 @@ def nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _deps():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "vt_b200.h")]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "vt_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build_lib(force=False, verbose=False, extra=()):
     if not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc()] + NVCC_FLAGS + list(extra) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    # use the system host compiler; the image exports CXX/CC pointing at a wrapper nvcc cannot use
-    env = dict(os.environ)
-    cmd += ["-ccbin", "/usr/bin/g++"]
-    subprocess.check_call(cmd, env=env)
+    os.makedirs(OBJDIR, exist_ok=True)
+    sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    headers_t = max(os.path.getmtime(d) for d in _deps() if d.endswith(".h"))
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, src[:-3] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), headers_t):
+            return obj, ""
+        cmd = [nvcc()] + COMPILE_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + HOST_CXX + ["-c", path, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return obj, r.stdout + r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, sources))
+    for _, log in results:
+        if log.strip():
+            print(log.rstrip(), file=sys.stderr if not verbose else sys.stdout)
+    link = [nvcc()] + ARCH_FLAGS + ["--shared", "-cudart", "shared"] + HOST_CXX + ["-o", LIB] + [o for o, _ in results]
+    subprocess.check_call(link)
     return LIB
 
 
