@@ -213,6 +213,8 @@ def run_gpu(args):
         runner = None
         ctx = vtb.Context(local)
         mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"], brick=tuple(args.brick))
+        if args.pencil:                    # experiment: pencil sweep instead of bricks (N=1 only)
+            mt.order, mt.brickTets = synthetic.pencil_order(*hexes, args.pencil[0], args.pencil[1])
         ctx.mesh_upload(mt)
         sp = ctx.species_create(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
         ctx.set_face_bc(sp, np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8))
@@ -326,7 +328,8 @@ def run_gpu(args):
                 "workload": workload_name(hexes, nv),
                 "tets_per_gpu": nT, "v_nodes": N, "state_bytes_per_gpu": 2 * nT * N * 8,
                 "l2_policy": "inputs larger than L2 (state is %.1f GB per copy); no flush needed" % (nT * N * 8 / 1e9),
-                "brick_hexes": list(args.brick), "chunk_planes": args.chunk_planes, "kernel_variant": args.variant,
+                "brick_hexes": list(args.brick) if not (args.pencil and world == 1) else None,
+                "pencil_hexes": args.pencil if world == 1 else None, "chunk_planes": args.chunk_planes, "kernel_variant": args.variant,
                 "kernel": kernel_name,
                 "step": "K1 full_step (flux+accel+Euler+density partials) + density reduce" + ("; halo push over NVLink" if world > 1 else ""),
             },
@@ -361,6 +364,8 @@ def main():
     ap.add_argument("--hexes", type=int, nargs=3, default=[28, 28, 28], help="hexes per GPU block")
     ap.add_argument("--nv", type=int, default=32)
     ap.add_argument("--brick", type=int, nargs=3, default=[4, 4, 4], help="L2 brick in hexes")
+    ap.add_argument("--pencil", type=int, nargs=2, default=None, metavar=("A", "DEPTH"),
+                    help="experiment: order tets in AxA-hex pencils swept along z (bricks of AxAxDEPTH)")
     ap.add_argument("--chunk-planes", type=int, default=0, help="i2-planes per work item (0 = whole tensor)")
     ap.add_argument("--variant", type=int, default=64,
                     help="vt_step_config variant bits; 64 = the library's own choice (bulk-copy pipeline, upwind-select "

@@ -29,11 +29,19 @@ def main():
     peak, _ = bench.measured_peak()
     out = open(args.out, "a")
     for bs in args.bricks.split(";"):
-        brick = tuple(int(x) for x in bs.split(","))
-        if any(h % b for h, b in zip(hexes, brick)):
-            continue
+        if bs.startswith("p"):             # "pA,D": A x A-hex pencils swept along z, bricks of A x A x D
+            a, depth = (int(x) for x in bs[1:].split(","))
+            if hexes[0] % a or hexes[1] % a or hexes[2] % depth:
+                continue
+            brick = ("pencil", a, depth)
+            mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"])
+            mt.order, mt.brickTets = synthetic.pencil_order(*hexes, a, depth)
+        else:
+            brick = tuple(int(x) for x in bs.split(","))
+            if any(h % b for h, b in zip(hexes, brick)):
+                continue
+            mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"], brick=brick)
         ctx = vtb.Context(0)
-        mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"], brick=brick)
         ctx.mesh_upload(mt)
         sp = ctx.species_create(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
         ctx.set_face_bc(sp, np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8))

@@ -83,6 +83,25 @@ def test_brick_order_is_a_permutation_of_compact_bricks():
     assert (c.max(0) - c.min(0)).max() < 0.5 + 1e-12     # first brick spans 3 of 6 cells per axis
 
 
+def test_pencil_order_sweeps_contiguously():
+    """pencil_order: a permutation; every brick is one a x a x depth block of hexes; consecutive bricks
+    touch (the sweep never jumps), which is what keeps the rows in flight next to the cached ones."""
+    from vlasovtucker_b200 import synthetic
+    nx = ny = nz = 6
+    mt = synthetic.periodic_kuhn_tables(nx, ny, nz)
+    order, bt = synthetic.pencil_order(nx, ny, nz, 2, 3)
+    assert sorted(order.tolist()) == list(range(mt.nTets)) and bt == 6 * 2 * 2 * 3
+    cen = mt.tetCentroid[order].reshape(-1, bt, 3)
+    ext = cen.max(1) - cen.min(1)
+    assert (ext[:, :2] < 2 / 6).all() and (ext[:, 2] < 3 / 6).all()
+    mid = cen.mean(1)
+    step = np.abs(np.diff(mid, axis=0))
+    assert (step.max(1) <= 3 / 6 + 1e-12).all()            # next brick is an x, y or z neighbour
+    assert ((step > 1e-12).sum(1) == 1).all()
+    with pytest.raises(ValueError):
+        synthetic.pencil_order(6, 6, 6, 4)
+
+
 def test_header_is_plain_c():
     """The drop-in boundary is a C ABI: the header compiles as C99 and as C++ without any CUDA or
     torch type in a signature."""

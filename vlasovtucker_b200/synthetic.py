@@ -134,6 +134,24 @@ def brick_order(nx, ny, nz, brick):
     return order.astype(np.int32), 6 * bx * by * bz
 
 
+def pencil_order(nx, ny, nz, a, depth=1):
+    """Locality permutation for the Kuhn box that sweeps a x a-hex pencils along z, back and forth,
+    the pencils themselves in serpentine order: the rows in flight always border the rows just
+    processed, so only the four side faces of a pencil miss the cache (scripts/prototypes/
+    l2_order_model.py).  Returns (order, tets_per_brick) with bricks of a*a*depth hexes."""
+    if nx % a or ny % a or nz % depth:
+        raise ValueError("pencil dims must divide the box dims")
+    hk, hj, hi = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    hi, hj, hk = hi.ravel(), hj.ravel(), hk.ravel()
+    pi, pj = hi // a, hj // a
+    npj = ny // a
+    pen = pi * npj + np.where(pi % 2 == 0, pj, npj - 1 - pj)
+    kk = np.where(pen % 2 == 0, hk, nz - 1 - hk)
+    ho = np.lexsort(np.stack([hi % a, hj % a, kk, pen], 0))                          # last key is primary
+    order = (ho[:, None] * 6 + np.arange(6)[None, :]).reshape(-1)
+    return order.astype(np.int32), 6 * a * a * depth
+
+
 def periodic_kuhn_tables(nx, ny, nz, lengths=(1.0, 1.0, 1.0), brick=None):
     """Fully periodic Kuhn box as MeshTables (entities 1-6 are periodic pairs {1,2},{3,4},{5,6})."""
     nodes, tets, tris, ents = kuhn_box(nx, ny, nz, lengths)
