@@ -1,6 +1,7 @@
 """Prototype (CPU, numpy) for the next Tucker eigen-solve: tridiagonalise the unit-trace Gram matrix,
 find only the eigenvalues above the rank threshold by Sturm-sequence bisection (one eigenvalue index
 per lane on the device), get their vectors by inverse iteration + Gram-Schmidt, back-transform.
+A division-free Sturm count (sturm_count_nodiv) is checked alongside.
 Checked here against numpy.linalg.eigh on Gram matrices of states produced by the dense Tucker step
 (tests/tucker_dense_ref.py): same rank decisions, projector difference at rounding level.
 
@@ -52,6 +53,26 @@ def sturm_count(d, e2, x):
             q = 1e-300
         if q < 0:
             cnt += 1
+    return cnt
+
+
+def sturm_count_nodiv(d, e2, x):
+    """The same count without the division (a DP division per step is what would make the device
+    version slow): signs of the leading principal minors p_i = (d_i - x) p_{i-1} - e_i^2 p_{i-2},
+    rescaled by a power of two when they drift.  Agrees with sturm_count for every x above the
+    rounding level of the matrix (checked in main)."""
+    cnt, pm2, pm1 = 0, 0.0, 1.0
+    for i in range(len(d)):
+        p = (d[i] - x) * pm1 - (e2[i] * pm2 if i > 0 else 0.0)
+        if p == 0.0:
+            p = -1e-300 if pm1 > 0 else 1e-300
+        if (p < 0) != (pm1 < 0):
+            cnt += 1
+        m = max(abs(p), abs(pm1))
+        if m < 1e-100 or m > 1e100:
+            sc = 2.0 ** (-np.frexp(m)[1])
+            p, pm1 = p * sc, pm1 * sc
+        pm2, pm1 = pm1, p
     return cnt
 
 
@@ -139,6 +160,9 @@ def main():
                 for k in range(3):
                     M = tdr.unfold(X, k)
                     G = M @ M.T
+                    dd, ee, _ = householder_tridiag(G / np.trace(G))
+                    for x in 10.0 ** rng.uniform(-15, 0, 20):
+                        assert sturm_count(dd, ee * ee, x) == sturm_count_nodiv(dd, ee * ee, x)
                     lr, Vr = reference(G, eps, max(n))
                     lp, Vp = leading_eigs(G, eps, max(n))
                     assert len(lr) == len(lp), (n, trial, eps, k, len(lr), len(lp))
