@@ -1,0 +1,21 @@
+"""Keeps the CPU-checked prototypes under scripts/prototypes/ honest: the device-style leading-eigenpair
+solver planned for the Tucker rounding (eig_leading.h) against numpy on its whole case list."""
+import importlib.util
+import os
+
+from conftest import ROOT
+
+
+def _load(name):
+    path = os.path.join(ROOT, "scripts", "prototypes", name + ".py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_leading_eigenpairs_prototype_matches_numpy(capsys):
+    mod = _load("eig_leading_check")
+    mod.main()
+    out = capsys.readouterr().out
+    assert out.startswith("cases 270")
