@@ -94,6 +94,13 @@ def _run_pair(vt, oracle_mod, m, n, vmin, vmax, mass, charge, f0, E, dt, steps, 
     ((32, 32, 4), 2, 0, 0),               # register-staged kernel, reference expression shape
     ((64, 64, 3), None, 0, 18),           # 4 columns per consumer thread, 32 KiB planes (ring depth 1x... 4)
     ((24, 22, 4), 3, 0, 16),              # plane not a multiple of the consumer count, reference arithmetic
+    ((32, 32, 4), None, 0, 64 | 128),     # default kernel with whole neighbour planes by bulk copy (round-1 path)
+    ((32, 32, 7), 3, 64, 50),             # consumer-side neighbour loads, ragged chunks, bricks
+    ((32, 32, 8), 2, 0, 50 | 256),        # ... work items in tet-major order, chunk fastest
+    ((32, 32, 3), 1, 0, 50 | 256),        # ... single-plane items: the neighbour prefetch runs across 3 items
+    ((64, 16, 5), None, 0, None),         # eight-warp layout on a non-square plane (no compile-time shape)
+    ((16, 64, 6), 4, 0, 64 | 256),
+    ((64, 16, 5), None, 0, 64 | 128),
 ])
 def test_update_pdf_periodic_parity(vt, oracle_mod, n, chunk, brick, variant):
     m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(1, 2), (3, 4), (5, 6)])
@@ -113,6 +120,41 @@ def test_update_pdf_periodic_parity(vt, oracle_mod, n, chunk, brick, variant):
     assert rel_l2(ctx.density(g), s.density(sp)) <= TOL
     assert np.abs(ctx.velocity(g) - s.velocity(sp)).max() <= 1e-9 * np.abs(s.velocity(sp)).max()
     ctx.close()
+
+
+@pytest.mark.parametrize("vmin,vmax", [([0.5, -0.1, -0.3], [3, 0.4, -0.05]), ([-3, -2, 1e-3], [-1, 2, 4]),
+                                       ([-1e-9, -1e-9, -1e-9], [1e-9, 1e-9, 1e-9]), ([-2e6, -2e6, -2e6], [2e6, 2e6, 2e6])])
+def test_inflow_only_neighbour_loads_on_lopsided_grids(vt, oracle_mod, vmin, vmax):
+    """The default kernel at 32x32 planes loads a neighbour value only where v.n <= 0 (single-precision
+    predicate with a guard band).  Grids that do not straddle v = 0, and very small / large velocity
+    scales, move the inflow boundary to the edges of the planes or out of them."""
+    m = oracle_mod.Mesh.load(mesh_path("rectangle.msh"), [(1, 2), (3, 4), (5, 6)])
+    n = (32, 32, 6)
+    f0 = _smooth_state(m, n, vmin, vmax, seed=2)
+    scale = max(abs(x) for x in vmin + vmax)
+    h = m.tetVolume.min() ** (1.0 / 3.0)
+    dt = 0.05 * h / scale
+    E = np.zeros((m.nTets, 3))
+    s, sp, ctx, g = _run_pair(vt, oracle_mod, m, n, vmin, vmax, 1.0, 1.0, f0, E, dt, 3,
+                              order=np.random.default_rng(1).permutation(m.nTets).astype(np.int32))
+    for _ in range(3):
+        s.update_pdf(sp, E)
+        ctx.step_full(g, dt)
+    assert rel_l2(ctx.get_pdf(g), s.get_pdf(sp)) <= TOL
+    # and bit-identical to the same kernel fed with whole neighbour planes
+    ctx2 = vt.Context(0)
+    ctx2.mesh_upload(tables_from_oracle(m))
+    g2 = ctx2.species_create(n, vmin, vmax, 1.0, 1.0)
+    bc, col = face_bc_arrays(m, {})
+    ctx2.set_face_bc(g2, bc, col)
+    ctx2.set_pdf(g2, f0)
+    ctx2.step_config(variant=64 | 128)
+    ctx2.field_set(E)
+    for _ in range(3):
+        ctx2.step_full(g2, dt)
+    assert np.array_equal(ctx2.get_pdf(g2), ctx.get_pdf(g))
+    ctx.close()
+    ctx2.close()
 
 
 def test_c1_delta_one_step(vt, oracle_mod):
@@ -160,7 +202,8 @@ def test_maxwellian_init_bit_exact(vt, oracle_mod):
     ctx.close()
 
 
-@pytest.mark.parametrize("n,variant", [((50, 5, 5), None), ((32, 16, 5), 18), ((32, 32, 4), 50)])
+@pytest.mark.parametrize("n,variant", [((50, 5, 5), None), ((32, 16, 5), 18), ((32, 32, 4), 50), ((32, 32, 4), 50 | 128),
+                                       ((64, 16, 3), None)])
 def test_wall_bcs_and_charge(vt, oracle_mod, n, variant):
     """Sheath-style boundaries (examples/sheath.cpp:100-110): entity 1 Absorbing+collectCharge,
     entity 2 Free, {3,4},{5,6} periodic; wall charge as solver.cpp:171-178."""
@@ -183,7 +226,7 @@ def test_wall_bcs_and_charge(vt, oracle_mod, n, variant):
     ctx.close()
 
 
-@pytest.mark.parametrize("n,variant", [((8, 6, 4), None), ((32, 16, 4), 18)])
+@pytest.mark.parametrize("n,variant", [((8, 6, 4), None), ((32, 16, 4), 18), ((32, 32, 4), None), ((32, 32, 4), 50 | 128)])
 def test_source_bc(vt, oracle_mod, n, variant):
     """Source faces use ParticleBC::sourcePDF in place of the neighbour (solver.cpp:334-339)."""
     m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(3, 4), (5, 6)])

@@ -361,7 +361,8 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
     if (ctx->variant & 64) {
         const int PE = sp.n[0] * sp.n[1];
         const bool planes = sp.n[0] % 2 == 0 && PE * 8 >= 4096 && PE / 2 <= 2048;
-        ctx->variant = planes ? (2 | 16 | 32) : 2;
+        // bits 7 and up are modifiers of the bulk-copy pipeline and stay as given
+        ctx->variant = (ctx->variant & ~127) | (planes ? (2 | 16 | 32) : 2);
     }
     StepParams p;
     p.f = sp.f[sp.cur];

@@ -80,6 +80,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// 16-byte async copy global -> shared through the LSU (SASS LDGSTS.BYPASS), L2 only
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -97,25 +109,6 @@ struct ItemHdr {
     double pad;
 };
 
-// Work item w of a launch over nTets tets (all owned tets, or the sub-list tetList of them):
-// brick-major, then chunk, then tet.
-__device__ __forceinline__ bool decode_item(const StepParams& p, const int* __restrict__ tetList, int nTets, long long w,
-                                            long long total, ItemHdr& it)
-{
-    if (w >= total) return false;
-    const int perBrick = p.brickTets * p.nChunks;
-    const int brick = (int)(w / perBrick);
-    const int base = brick * p.brickTets;
-    const int nb = min(p.brickTets, nTets - base);
-    const int r = (int)(w - (long long)brick * perBrick);
-    it.chunk = r / nb;
-    const int pos = base + (r - it.chunk * nb);
-    it.tet = tetList ? tetList[pos] : pos;
-    it.pl0 = it.chunk * p.chunkPlanes;
-    it.npl = min(p.chunkPlanes, p.n2 - it.pl0);
-    return true;
-}
-
 struct BulkParams {
     StepParams s;
     int OD, S;        // own ring depth (planes), neighbour ring depth (4-plane sets)
@@ -125,7 +118,39 @@ struct BulkParams {
     long long total;
     const int* tetList;   // nullptr: all owned tets in device order
     int nTets;
+    int orderMode;    // 0: brick, chunk, tet (tet fastest); 1: tet, chunk (chunk fastest)
+    // single-precision copies for the neighbour-load predicate (consumer-side loads only)
+    float vmin0f, vmin1f, vmin2f, step0f, step1f, step2f, guard;
 };
+
+// Work item w of a launch over nTets tets (all owned tets, or the sub-list tetList of them).
+// orderMode 0: brick-major, then chunk, then tet — all SMs sweep one velocity window of one brick;
+// orderMode 1: tet-major, chunk fastest — the chunks of one tet are in flight on neighbouring CTAs at
+// the same time, so the rows in flight are total/nChunks tets and the i2 halo planes two chunks share
+// are fetched from DRAM once.
+__device__ __forceinline__ bool decode_item(const BulkParams& P, long long w64, ItemHdr& it)
+{
+    if (w64 >= P.total) return false;
+    const StepParams& p = P.s;
+    const unsigned w = (unsigned)w64;   // total < 2^31 (checked by the launcher)
+    int pos;
+    if (P.orderMode == 1) {
+        pos = (int)(w / (unsigned)p.nChunks);
+        it.chunk = (int)(w - (unsigned)pos * (unsigned)p.nChunks);
+    } else {
+        const unsigned perBrick = (unsigned)p.brickTets * (unsigned)p.nChunks;
+        const unsigned brick = w / perBrick;
+        const int base = (int)(brick * (unsigned)p.brickTets);
+        const int nb = min(p.brickTets, P.nTets - base);
+        const unsigned r = w - brick * perBrick;
+        it.chunk = (int)(r / (unsigned)nb);
+        pos = base + (int)(r - (unsigned)it.chunk * (unsigned)nb);
+    }
+    it.tet = P.tetList ? P.tetList[pos] : pos;
+    it.pl0 = it.chunk * p.chunkPlanes;
+    it.npl = min(p.chunkPlanes, p.n2 - it.pl0);
+    return true;
+}
 
 struct Smem {
     double* ownRing;     // [OD][PE]
@@ -148,7 +173,10 @@ struct Cursor {
     }
 };
 
-// ---- producer: one thread; claims items from the queue and keeps both rings full
+// ---- producer: one thread; claims items from the queue and keeps the rings full.
+// NBRCP: the consumers fetch the neighbour values themselves (see NbrFetch), the producer streams
+// the own planes only and never has to wait for a tet record.
+template <bool NBRCP>
 __device__ void producer_loop(const BulkParams& P, const Smem& sm)
 {
     const StepParams& p = P.s;
@@ -161,10 +189,9 @@ __device__ void producer_loop(const BulkParams& P, const Smem& sm)
     // (finish_item) so that their latency is never waited for.
     double ePend[3] = {0.0, 0.0, 0.0};
     int pendSlot = -1;
-    auto post_item = [&](long long w) {   // header + tet record of the item into slot cPost
+    auto post_item = [&](long long w, ItemHdr& h) {   // header + tet record of the item into slot cPost
         mbar_wait(sm.itemEmpty + cPost.slot, cPost.phase ^ 1u);
-        ItemHdr h;
-        if (decode_item(p, P.tetList, P.nTets, w, P.total, h)) {
+        if (decode_item(P, w, h)) {
             sm.hdr[cPost.slot].tet = h.tet;
             sm.hdr[cPost.slot].chunk = h.chunk;
             sm.hdr[cPost.slot].pl0 = h.pl0;
@@ -174,6 +201,7 @@ __device__ void producer_loop(const BulkParams& P, const Smem& sm)
             mbar_expect_tx(sm.itemFull + cPost.slot, (uint32_t)sizeof(TetRec));
             bulk_g2s(sm.rec + cPost.slot, p.rec + h.tet, (uint32_t)sizeof(TetRec), sm.itemFull + cPost.slot);
         } else {
+            h.tet = -1;
             sm.hdr[cPost.slot].tet = -1;
             mbar_arrive(sm.itemFull + cPost.slot);
         }
@@ -186,26 +214,27 @@ __device__ void producer_loop(const BulkParams& P, const Smem& sm)
         mbar_arrive(sm.itemFull + pendSlot);
     };
 
+    ItemHdr h, hNext;
     long long wNext = (long long)atomicAdd(P.queue, 1ULL);
-    post_item(wNext);
+    post_item(wNext, h);
     wNext = (long long)atomicAdd(P.queue, 1ULL);
     while (true) {
         finish_item();                                      // item k
-        post_item(wNext);                                   // item k+1: its record lands while item k streams
+        post_item(wNext, hNext);                            // item k+1: its record lands while item k streams
         wNext = (long long)atomicAdd(P.queue, 1ULL);        // item k+2: the ticket is used one iteration later
-        mbar_wait(sm.itemFull + cItem.slot, cItem.phase);
-        const ItemHdr h = sm.hdr[cItem.slot];
         if (h.tet < 0) break;
-        const TetRec& r = sm.rec[cItem.slot];
-        const double* rows[4];
+        const double* rows[4] = {nullptr, nullptr, nullptr, nullptr};
         int cnt = 0;
+        if (!NBRCP) {
+            mbar_wait(sm.itemFull + cItem.slot, cItem.phase);
+            const TetRec& r = sm.rec[cItem.slot];
 #pragma unroll
-        for (int f = 0; f < 4; f++) {
-            rows[f] = nullptr;
-            if (is_pair(r.bc[f])) {
-                const int n = r.nbr[f];
-                rows[f] = n >= 0 ? p.f + (size_t)n * p.N : p.src + (size_t)(-2 - n) * p.N;
-                cnt++;
+            for (int f = 0; f < 4; f++) {
+                if (is_pair(r.bc[f])) {
+                    const int n = r.nbr[f];
+                    rows[f] = n >= 0 ? p.f + (size_t)n * p.N : p.src + (size_t)(-2 - n) * p.N;
+                    cnt++;
+                }
             }
         }
         const double* own = p.f + (size_t)h.tet * p.N;
@@ -217,7 +246,7 @@ __device__ void producer_loop(const BulkParams& P, const Smem& sm)
             mbar_expect_tx(sm.ownFull + cOwn.slot, PB);
             bulk_g2s(sm.ownRing + (size_t)cOwn.slot * PE, own + (size_t)ip * PE, PB, sm.ownFull + cOwn.slot);
             cOwn.advance(P.OD);
-            if (s >= 1 && s <= h.npl) {
+            if (!NBRCP && s >= 1 && s <= h.npl) {
                 const size_t plane = (size_t)(h.pl0 + s - 1) * PE;
                 uint64_t* bar = sm.nbrFull + cNbr.slot;
                 mbar_wait(sm.nbrEmpty + cNbr.slot, cNbr.phase ^ 1u);
@@ -230,6 +259,7 @@ __device__ void producer_loop(const BulkParams& P, const Smem& sm)
             }
         }
         cItem.advance(kItemRing);
+        h = hNext;
     }
 }
 
@@ -284,9 +314,86 @@ struct ConsRings {
     uint32_t odMask, odShift, sMask, sShift;
 };
 
-template <int KPT, bool UPWIND, bool GENERIC, int NCW, int SN>
-__device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRings& R, const ItemHdr& cur, const TetRec& rec,
-                                             uint32_t& cOwn, uint32_t& cNbr, const Column (&col)[KPT])
+// ---- consumer-side neighbour loads (NBD > 0).
+// With the upwind-select flux a tet reads its neighbour across face f only where v.n_f <= 0 (inflow);
+// where v.n_f > 0 the flux uses the tet's own value.  On average that is half of every neighbour
+// row, and a bulk copy of whole planes moves the other half through L2 and the crossbar for
+// nothing — the round-1 kernel ran at 5,940 B/cycle of L2->SM traffic, the chip's limit.  Here every
+// consumer thread requests exactly the neighbour double2s its own columns will use, NBD-1 planes
+// ahead, as predicated 16-byte cp.async (LDGSTS, L2 only) into its private positions of the
+// neighbour ring; it is the only reader of those positions, so completion is the thread's own
+// cp.async group count and the ring needs no barrier at all.  The predicate is evaluated in single
+// precision with a guard band (BulkParams::guard) wide enough that every value the FP64 select can
+// pick has been requested; values in the guard band are loaded and not used.
+template <int KPT>
+struct NbrFetch {
+    int itemSlot = 0;
+    uint32_t itemPhase = 0;   // next item slot to open
+    int left = 0;             // planes of the open item not requested yet
+    bool done = false;        // the end-of-queue item has been seen
+    uint32_t cnt = 0;         // planes requested so far (ring slot = cnt & (NBD-1))
+    float v2 = 0.f;           // velocity of the next plane to request
+    const char* gp[4];        // neighbour row f at that plane, at the thread's first column
+    float cmin[KPT][4];       // min over the double2 of (n_x v0 + n_y v1), minus the guard; +inf: never load
+    float cz[4];              // n_z
+};
+
+template <int KPT, int NBD>
+__device__ __forceinline__ void nbr_fetch_plane(const BulkParams& P, const Smem& sm, const ConsRings& R, const uint32_t PB,
+                                                NbrFetch<KPT>& F, const uint32_t (&oEv)[KPT], const float (&vf)[KPT][3])
+{
+    const StepParams& p = P.s;
+    if (F.left == 0 && !F.done) {
+        mbar_wait(sm.itemFull + F.itemSlot, F.itemPhase);
+        const int tet = sm.hdr[F.itemSlot].tet;
+        if (tet < 0) {
+            F.done = true;
+        } else {
+            const TetRec& r = sm.rec[F.itemSlot];
+            const int pl0 = sm.hdr[F.itemSlot].pl0;
+            F.left = sm.hdr[F.itemSlot].npl;
+            F.v2 = fmaf((float)pl0, P.step2f, P.vmin2f);
+#pragma unroll
+            for (int f = 0; f < 4; f++) {
+                const int n = r.nbr[f];
+                const bool have = is_pair(r.bc[f]) && n != -1;
+                const double* row = n >= 0 ? p.f + (size_t)n * p.N : p.src + (size_t)(n <= -2 ? -2 - n : 0) * p.N;
+                F.gp[f] = reinterpret_cast<const char*>(row + (size_t)pl0 * P.planeElems) + oEv[0];
+                const float nx = (float)r.nrm[f][0], ny = (float)r.nrm[f][1];
+                F.cz[f] = (float)r.nrm[f][2];
+#pragma unroll
+                for (int kk = 0; kk < KPT; kk++)
+                    F.cmin[kk][f] = have ? fminf(nx * vf[kk][0], nx * vf[kk][1]) + ny * vf[kk][2] - P.guard : INFINITY;
+            }
+        }
+        if (++F.itemSlot == kItemRing) {
+            F.itemSlot = 0;
+            F.itemPhase ^= 1u;
+        }
+    }
+    if (F.left > 0) {
+        const uint32_t dst0 = R.nbr + (F.cnt & (uint32_t)(NBD - 1)) * 4u * PB + oEv[0];
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+#pragma unroll
+            for (int kk = 0; kk < KPT; kk++) {
+                const float t = fmaf(F.cz[f], F.v2, F.cmin[kk][f]);
+                const uint32_t d = oEv[kk] - oEv[0];
+                if (t <= 0.f) cp_async16(dst0 + (uint32_t)f * PB + d, F.gp[f] + d);
+            }
+            F.gp[f] += PB;
+        }
+        F.v2 += P.step2f;
+        F.left--;
+    }
+    F.cnt++;
+    cp_async_commit();
+}
+
+template <int KPT, bool UPWIND, bool GENERIC, int NCW, int SN, int NBD>
+__device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm, const ConsRings& R, const ItemHdr& cur,
+                                             const TetRec& rec, uint32_t& cOwn, uint32_t& cNbr, const Column (&col)[KPT],
+                                             const uint32_t (&oEv)[KPT], NbrFetch<KPT>& F, const float (&vf)[KPT][3])
 {
     const StepParams& p = P.s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -322,7 +429,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
     char* outp[KPT];
 #pragma unroll
     for (int kk = 0; kk < KPT; kk++)
-        outp[kk] = reinterpret_cast<char*>(p.fn + (size_t)cur.tet * p.N + (size_t)cur.pl0 * P.planeElems) + col[kk].evB;
+        outp[kk] = reinterpret_cast<char*>(p.fn + (size_t)cur.tet * p.N + (size_t)cur.pl0 * P.planeElems) + oEv[kk];
     long long pushOff[4] = {0, 0, 0, 0};   // byte distance from this tet's row to its ghost copies
     bool pushOn[4] = {false, false, false, false};
     if (GENERIC) {
@@ -344,7 +451,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
         mbar_wait32(R.ownFull + slot * 8, (cOwn >> R.odShift) & 1u);
         const uint32_t a = R.own + slot * R.PB;
 #pragma unroll
-        for (int kk = 0; kk < KPT; kk++) prv[kk] = lds128(a + col[kk].evB);
+        for (int kk = 0; kk < KPT; kk++) prv[kk] = lds128(a + oEv[kk]);
         __syncwarp();
         if (lane == 0) mbar_arrive32(R.ownEmpty + slot * 8);
         cOwn++;
@@ -354,25 +461,20 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
     uint32_t scA = R.own + scSlot * R.PB;
     cOwn++;
 #pragma unroll
-    for (int kk = 0; kk < KPT; kk++) cr[kk] = lds128(scA + col[kk].evB);
+    for (int kk = 0; kk < KPT; kk++) cr[kk] = lds128(scA + oEv[kk]);
 
     // Per-thread byte offsets of the stencil operands.  With a compile-time plane shape (SN x SN) and
     // paired columns the second column is the first plus one row, so most addresses become
     // register + immediate.
     constexpr bool SPEC = SN > 0 && PAIRED;
     const uint32_t PB = SPEC ? (uint32_t)(SN * SN * 8) : R.PB;
-    uint32_t oEv[KPT], oUm[KPT], oUp[KPT], oFl[KPT], oFr[KPT];
+    uint32_t oUm[KPT], oUp[KPT], oFl[KPT], oFr[KPT];
 #pragma unroll
     for (int kk = 0; kk < KPT; kk++) {
-        oEv[kk] = (SPEC && kk == 1) ? col[0].evB + SN * 8 : col[kk].evB;
         oUm[kk] = col[kk].dUmB;
         oUp[kk] = col[kk].dUpB;
         oFl[kk] = (SPEC && kk == 1) ? col[0].dFlB + SN * 8 : col[kk].dFlB;
         oFr[kk] = (SPEC && kk == 1) ? col[0].dFrB + SN * 8 : col[kk].dFrB;
-    }
-    if (SPEC) {
-#pragma unroll
-        for (int kk = 1; kk < KPT; kk++) outp[kk] = outp[0] + SN * 8;
     }
 
     double2 nxt[KPT];
@@ -380,12 +482,15 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
     // One plane: pv/cv hold planes j-1 and j of the thread's columns, nv receives plane j+1.  The
     // plane loop below calls it with the three register sets rotating, so no values are moved.
     auto plane = [&](const double2 (&pv)[KPT], const double2 (&cv)[KPT], double2 (&nv)[KPT]) {
+        // request the neighbour values of plane j+NBD-1 (of this item or the next ones) before waiting
+        if (NBD > 0) nbr_fetch_plane<KPT, (NBD > 0 ? NBD : 1)>(P, sm, R, PB, F, oEv, vf);
         const uint32_t snSlot = cOwn & R.odMask;
         mbar_wait32(R.ownFull + snSlot * 8, (cOwn >> R.odShift) & 1u);
         const uint32_t snA = R.own + snSlot * PB;       // plane j+1
         cOwn++;
-        const uint32_t nbSlot = cNbr & R.sMask;
-        mbar_wait32(R.nbrFull + nbSlot * 8, (cNbr >> R.sShift) & 1u);
+        const uint32_t nbSlot = NBD > 0 ? (cNbr & (uint32_t)(NBD - 1)) : (cNbr & R.sMask);
+        if (NBD > 0) cp_async_wait<(NBD > 0 ? NBD - 1 : 0)>();
+        else mbar_wait32(R.nbrFull + nbSlot * 8, (cNbr >> R.sShift) & 1u);
         const uint32_t sbA = R.nbr + nbSlot * 4 * PB;
         cNbr++;
 
@@ -429,6 +534,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
                     const double fau = u == 0 ? fa[f].x : fa[f].y;
                     if (!GENERIC || pairF[f]) {
                         if (UPWIND) {
+                            // with NBD > 0 fau is defined only where vn <= 0 (plus the guard band)
                             rhs = fma(-vn, vn > 0.0 ? fv : fau, rhs);
                         } else {
                             const double s = __dadd_rn(fau, fv), d = __dsub_rn(fau, fv);
@@ -462,7 +568,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
         __syncwarp();   // every lane is done with own stage sc and neighbour slot nbSlot
         if (lane == 0) {
             mbar_arrive32(R.ownEmpty + scSlot * 8);
-            mbar_arrive32(R.nbrEmpty + nbSlot * 8);
+            if (NBD == 0) mbar_arrive32(R.nbrEmpty + nbSlot * 8);
         }
         scA = snA;
         scSlot = snSlot;
@@ -494,9 +600,12 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const ConsRing
     }
 }
 
-template <int KPT, bool UPWIND, int NCW, bool ALLFAST, int SN>
-__global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkParams P)
+// NBD = 0: the producer bulk-copies whole neighbour planes; NBD = 2 or 4: the consumers request the
+// neighbour values they use themselves, NBD-1 planes ahead (upwind-select arithmetic only).
+template <int KPT, bool UPWIND, int NCW, bool ALLFAST, int SN, int NBD>
+__global__ void __maxnreg__(NCW == 8 ? 224 : 112) k_full_step_bulk(const BulkParams P)
 {
+    static_assert(NBD == 0 || UPWIND, "consumer-side neighbour loads rely on the upwind select");
     const StepParams& p = P.s;
     extern __shared__ __align__(128) unsigned char smraw[];
     const int PE = P.planeElems;
@@ -531,12 +640,15 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
     __syncthreads();
 
     if (tid >= NCW * 32) {
-        if (tid == NCW * 32) producer_loop(P, sm);
+        if (tid == NCW * 32) producer_loop<(NBD > 0)>(P, sm);
         return;
     }
 
     // fixed columns of this consumer thread
+    constexpr bool SPEC = SN > 0 && KPT == 2 && NCW == 8;
     Column col[KPT];
+    uint32_t oEv[KPT];
+    float vf[KPT][3];   // v0(i0), v0(i0+1), v1(i1) of the column in single precision (neighbour-load predicate)
 #pragma unroll
     for (int kk = 0; kk < KPT; kk++) {
         // eight warps x two columns (launched only when the plane is exactly 2 x 256 double2 and n1 is
@@ -552,6 +664,10 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
         col[kk].dUpB = 8u * (uint32_t)(2 * cv + ((i1 == p.n1 - 1) ? -(p.n1 - 1) : 1) * p.n0);
         col[kk].dFlB = 8u * (uint32_t)(2 * cv + ((i0 == 0) ? (p.n0 - 1) : -1));
         col[kk].dFrB = 8u * (uint32_t)(2 * cv + 1 + ((i0 + 2 == p.n0) ? -(p.n0 - 1) : 1));
+        oEv[kk] = (SPEC && kk == 1) ? col[0].evB + SN * 8 : col[kk].evB;
+        vf[kk][0] = fmaf((float)i0, P.step0f, P.vmin0f);
+        vf[kk][1] = fmaf((float)(i0 + 1), P.step0f, P.vmin0f);
+        vf[kk][2] = fmaf((float)i1, P.step1f, P.vmin1f);
     }
     ConsRings R;
     R.own = smem_u32(sm.ownRing);
@@ -568,26 +684,34 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
     Cursor cItem;
     uint32_t cOwn = 0, cNbr = 0;
     const int lane = tid & 31;
+    NbrFetch<KPT> F;
+    if (NBD > 0) {
+        // prime the neighbour pipeline: planes 0 .. NBD-2 of the CTA's plane stream
+        const uint32_t PBk = SPEC ? (uint32_t)(SN * SN * 8) : R.PB;
+#pragma unroll 1
+        for (int d = 0; d < NBD - 1; d++) nbr_fetch_plane<KPT, (NBD > 0 ? NBD : 1)>(P, sm, R, PBk, F, oEv, vf);
+    }
     while (true) {
         mbar_wait(sm.itemFull + cItem.slot, cItem.phase);
         const ItemHdr cur = sm.hdr[cItem.slot];
         if (cur.tet < 0) break;
         const TetRec& rec = sm.rec[cItem.slot];
         if (ALLFAST) {
-            item_compute<KPT, UPWIND, false, NCW, SN>(P, R, cur, rec, cOwn, cNbr, col);
+            item_compute<KPT, UPWIND, false, NCW, SN, NBD>(P, sm, R, cur, rec, cOwn, cNbr, col, oEv, F, vf);
         } else {
             const bool fast = is_pair(rec.bc[0]) && is_pair(rec.bc[1]) && is_pair(rec.bc[2]) && is_pair(rec.bc[3]) &&
                               rec.pushPeer[0] < 0;
-            if (fast) item_compute<KPT, UPWIND, false, NCW, SN>(P, R, cur, rec, cOwn, cNbr, col);
-            else item_compute<KPT, UPWIND, true, NCW, SN>(P, R, cur, rec, cOwn, cNbr, col);
+            if (fast) item_compute<KPT, UPWIND, false, NCW, SN, NBD>(P, sm, R, cur, rec, cOwn, cNbr, col, oEv, F, vf);
+            else item_compute<KPT, UPWIND, true, NCW, SN, NBD>(P, sm, R, cur, rec, cOwn, cNbr, col, oEv, F, vf);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(sm.itemEmpty + cItem.slot);
         cItem.advance(kItemRing);
     }
+    if (NBD > 0) cp_async_wait<0>();
 }
 
-template <int KPT, int NCW, int SN>
+template <int KPT, int NCW, int SN, int NBD>
 void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, size_t smem, cudaStream_t stream, int maxCTAs)
 {
     if (P.total == 0) return;
@@ -598,8 +722,13 @@ void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, siz
         kern<<<grid, NCW * 32 + 32, smem, stream>>>(P);
         ctx->launches++;
     };
-    if (allFast) upwind ? launch(k_full_step_bulk<KPT, true, NCW, true, SN>) : launch(k_full_step_bulk<KPT, false, NCW, true, SN>);
-    else upwind ? launch(k_full_step_bulk<KPT, true, NCW, false, SN>) : launch(k_full_step_bulk<KPT, false, NCW, false, SN>);
+    if constexpr (NBD > 0) {
+        // consumer-side neighbour loads exist for the upwind-select arithmetic only
+        allFast ? launch(k_full_step_bulk<KPT, true, NCW, true, SN, NBD>) : launch(k_full_step_bulk<KPT, true, NCW, false, SN, NBD>);
+    } else {
+        if (allFast) upwind ? launch(k_full_step_bulk<KPT, true, NCW, true, SN, 0>) : launch(k_full_step_bulk<KPT, false, NCW, true, SN, 0>);
+        else upwind ? launch(k_full_step_bulk<KPT, true, NCW, false, SN, 0>) : launch(k_full_step_bulk<KPT, false, NCW, false, SN, 0>);
+    }
 }
 
 }  // namespace
@@ -619,15 +748,18 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     const int ncw = wide ? 8 : 16;
     const int kpt = (PV + ncw * 32 - 1) / (ncw * 32);
     if (kpt > 4) return false;
+    // variant bit 7 switches the consumer-side neighbour loads off (whole neighbour planes by bulk copy)
+    const bool nbrSelf = upwind && wide && !(ctx->variant & 128);
     const size_t PB = (size_t)PE * 8;
     const size_t fixed = kItemRing * (sizeof(TetRec) + sizeof(ItemHdr)) + (4 * kMaxRing + 2 * kItemRing) * 8 + 128;
     const size_t maxSmem = 227 * 1024;
     // ring depths are powers of two (the consumers derive slot and parity from a stage counter)
-    int S = kMaxRing, OD = kMaxRing;
+    int S = nbrSelf ? 4 : kMaxRing, OD = kMaxRing;
     while (S > 2 && (size_t)S * 4 * PB + (size_t)4 * PB + fixed > maxSmem) S /= 2;
     while (OD > 4 && (size_t)OD * PB + (size_t)S * 4 * PB + fixed > maxSmem) OD /= 2;
     if ((size_t)OD * PB + (size_t)S * 4 * PB + fixed > maxSmem) return false;
     const size_t smem = (size_t)OD * PB + (size_t)S * 4 * PB + fixed;
+    if ((long long)ctx->nOwned * p.nChunks > 2147483647LL) return false;
 
     if (sp.fastOnly < 0) {
         // Tets whose four faces are all paired with a neighbour (or source) row and that push no halo
@@ -661,6 +793,21 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     P.planeElems = PE;
     P.PV = PV;
     P.queue = ctx->workCounter;
+    // variant bit 8: work items in tet-major order, the chunks of one tet adjacent in the queue
+    P.orderMode = (ctx->variant & 256) ? 1 : 0;
+    P.vmin0f = (float)sp.vmin[0];
+    P.vmin1f = (float)sp.vmin[1];
+    P.vmin2f = (float)sp.vmin[2];
+    P.step0f = (float)sp.step[0];
+    P.step1f = (float)sp.step[1];
+    P.step2f = (float)sp.step[2];
+    {
+        double vs = 0;
+        for (int k = 0; k < 3; k++) vs += std::max(std::fabs(sp.vmin[k]), std::fabs(sp.vmax[k]));
+        // single-precision evaluation of n.v (unit normal) is good to ~1e-6 of this sum, including the
+        // running sum of v2 over a row; the band makes the predicate err on the side of loading
+        P.guard = (float)(1e-4 * vs);
+    }
 
     const int sms = ctx->prop.multiProcessorCount;
     auto run = [&](const int* list, int nTets, bool allFast, cudaStream_t stream, int maxCTAs, int counter) {
@@ -668,12 +815,17 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
         P.nTets = nTets;
         P.total = (long long)nTets * p.nChunks;
         P.queue = ctx->workCounter + counter;
-        if (wide && n0 == 32 && n1 == 32) launch_cfg<2, 8, 32>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else if (wide) launch_cfg<2, 8, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else if (kpt == 1) launch_cfg<1, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else if (kpt == 2) launch_cfg<2, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else if (kpt == 3) launch_cfg<3, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
-        else launch_cfg<4, 16, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        if (wide && n0 == 32 && n1 == 32) {
+            if (nbrSelf && S == 4) launch_cfg<2, 8, 32, 4>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+            else launch_cfg<2, 8, 32, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        } else if (wide) {
+            if (nbrSelf && S == 4) launch_cfg<2, 8, 0, 4>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+            else if (nbrSelf && S == 2) launch_cfg<2, 8, 0, 2>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+            else launch_cfg<2, 8, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        } else if (kpt == 1) launch_cfg<1, 16, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 2) launch_cfg<2, 16, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else if (kpt == 3) launch_cfg<3, 16, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        else launch_cfg<4, 16, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
     };
     VT_CUDA(cudaEventRecord(e0, ctx->stream));
     if (sp.fastOnly == 1) {
