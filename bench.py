@@ -127,7 +127,7 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fused=False):
+def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fused=False, keep=None):
     """The oracle's reference-faithful restatement of _UpdatePDF (one temporary per tensor
     operator, OpenMP over tets as src/solver.cpp:159,187,204) on a bounded sample of C4."""
     threads = threads or os.cpu_count() or 1
@@ -156,10 +156,43 @@ def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fus
         s.update_pdf(sp, E)
     dt = (time.perf_counter() - t0) / steps
     updates = m.nTets * nv ** 3
+    if keep is not None:    # hand the oracle's end state to the parity check (bench line key "parity")
+        keep.update(sim=s, species=sp, mesh=m, steps_done=warmup + steps, cfg=cfg, E=E, hexes=hexes, nv=nv)
     return dict(value=updates / dt, unit="updates/s", cores=threads, kind="port",
                 sample=f"Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]}x6={m.nTets} tets x {nv}^3, "
                        f"{steps} timed _UpdatePDF steps ({'fused single-pass' if fused else 'reference-faithful temporaries'}, "
                        f"OpenMP {threads} threads)", ms_per_step=dt * 1e3)
+
+
+def parity_vs_oracle(keep, device, variant, chunk_planes):
+    """The bench kernel (same variant, same items) against the oracle on the CPU-baseline sample:
+    the oracle has just advanced that mesh by `steps_done` steps; do the same on the GPU from the
+    same initial condition and compare the end states (tolerance of north_star: rel. L2 <= 1e-10)."""
+    import vlasovtucker_b200 as vtb
+    from vlasovtucker_b200 import synthetic
+    cfg, hexes, m = keep["cfg"], keep["hexes"], keep["mesh"]
+    mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"], brick=(4, 4, 4))
+    ctx = vtb.Context(device)
+    ctx.mesh_upload(mt)
+    sp = ctx.species_create(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
+    ctx.set_face_bc(sp, np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8))
+    x = m.tetCentroid[:, 0] / cfg["lengths"][0]
+    ctx.set_maxwell(sp, cfg["dens"] * (1 + 0.01 * np.sin(2 * PI * x)), cfg["T"])
+    ctx.field_set(keep["E"])
+    ctx.step_config(chunk_planes=chunk_planes, variant=variant)
+    for _ in range(keep["steps_done"]):
+        ctx.step_full(sp, cfg["dt"])
+    s, osp = keep["sim"], keep["species"]
+    fo = s.get_pdf(osp)
+    fg = ctx.get_pdf(sp)
+    ef = float(np.linalg.norm((fg - fo).ravel()) / np.linalg.norm(fo.ravel()))
+    do, dg = s.density(osp), ctx.density(sp)
+    ed = float(np.linalg.norm(dg - do) / np.linalg.norm(do))
+    ctx.close()
+    return {"rel_l2_f": ef, "rel_l2_density": ed, "steps": int(keep["steps_done"]), "tolerance": 1e-10,
+            "ok": bool(ef <= 1e-10 and ed <= 1e-10),
+            "what": f"bench kernel (variant {variant}, chunk_planes {chunk_planes}) vs the CPU oracle on the cpu_baseline sample "
+                    f"({hexes[0]}x{hexes[1]}x{hexes[2]}x6 tets x {keep['nv']}^3), same initial condition and field"}
 
 
 def workload_name(hexes, nv):
@@ -347,8 +380,13 @@ def run_gpu(args):
         if coupled is not None:
             line["coupled_loop"] = coupled
         if not args.no_cpu_baseline and world == 1:
-            cb = cpu_baseline()
+            keep = {}
+            cb = cpu_baseline(keep=keep)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            try:
+                line["parity"] = parity_vs_oracle(keep, local, args.variant, args.chunk_planes)
+            except Exception as exc:
+                line["parity"] = {"error": str(exc)[:300]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

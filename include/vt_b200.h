@@ -142,6 +142,12 @@ int vt_profile_end(vt_ctx* ctx, float* region_ms, float* step_kernel_ms, int* st
 int vt_halo_export(vt_ctx* ctx, int species, void* handles);
 int vt_halo_attach(vt_ctx* ctx, int species, int myRank, int nPeers, const int32_t* peerRanks,
                    const void* peerHandles);
+/* the same wiring for contexts of ONE process — several devices with peer access driven by one host
+ * thread (the C++ Solver under VT_DEVICES), or several "virtual ranks" on one device (tests on a
+ * one-GPU box): the ghost rows point straight at the peers' buffers, no CUDA IPC involved.
+ * peerSpecies[i] is the species id of the same species in peerCtx[i]. */
+int vt_halo_attach_local(vt_ctx* ctx, int species, int myRank, int nPeers, const int32_t* peerRanks,
+                         vt_ctx* const* peerCtx, const int32_t* peerSpecies);
 int vt_halo_set_push(vt_ctx* ctx, int species, const int32_t* pushPeer, const int32_t* pushRow);
 int vt_halo_push_current(vt_ctx* ctx, int species);
 int vt_halo_barrier(vt_ctx* ctx);
@@ -192,6 +198,9 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3]);
  * vt_halo_push_current / vt_halo_barrier serve the species as they do for the full format. */
 int vt_tucker_halo_export(vt_ctx* ctx, int species, void* handle);
 int vt_tucker_halo_attach(vt_ctx* ctx, int species, int nPeers, const void* peerHandles);
+/* in-process counterpart (after vt_halo_attach_local with the same peers) */
+int vt_tucker_halo_attach_local(vt_ctx* ctx, int species, int nPeers, vt_ctx* const* peerCtx,
+                                const int32_t* peerSpecies);
 
 #ifdef __cplusplus
 }

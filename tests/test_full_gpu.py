@@ -296,8 +296,42 @@ def test_step_host_roundtrip(vt, oracle_mod):
     ctx.close()
 
 
+def test_bench_configuration_against_oracle(vt, oracle_mod):
+    """The exact bench configuration — 32^3 velocity grid, whole-tensor work items (chunk 0), the
+    library's default kernel, C4 physics (bench.c4_setup) — on the 8x8x8-hex Kuhn box, against the
+    oracle after 3 steps: state and density to relative L2 <= 1e-10."""
+    import bench
+    from vlasovtucker_b200 import synthetic
+    hexes, nv = (8, 8, 8), 32
+    cfg = bench.c4_setup(hexes, nv)
+    nodes, tets, tris, ents = synthetic.kuhn_box(*hexes, cfg["lengths"])
+    m = oracle_mod.Mesh.from_arrays(nodes, tets, tris, ents, [(1, 2), (3, 4), (5, 6)])
+    s = oracle_mod.Sim(m)
+    sp = s.add_species(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
+    x = m.tetCentroid[:, 0] / cfg["lengths"][0]
+    dens0 = cfg["dens"] * (1 + 0.01 * np.sin(2 * PI * x))
+    s.set_maxwell(sp, dens0, cfg["T"])
+    s.set_params(sp, cfg["dt"], fused=True)
+    E = np.zeros((m.nTets, 3))
+    E[:, 0] = 1e3 * np.cos(2 * PI * x)
+    mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"], brick=(4, 4, 4))
+    ctx = vt.Context(0)
+    ctx.mesh_upload(mt)
+    g = ctx.species_create(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
+    ctx.set_face_bc(g, np.full((mt.nTets, 4), vt.PBC["Periodic"], np.uint8))
+    ctx.set_maxwell(g, dens0, cfg["T"])
+    ctx.field_set(E)
+    ctx.step_config(chunk_planes=0, variant=64)
+    for _ in range(3):
+        s.update_pdf(sp, E)
+        ctx.step_full(g, cfg["dt"])
+    assert rel_l2(ctx.get_pdf(g), s.get_pdf(sp)) <= TOL
+    assert rel_l2(ctx.density(g), s.density(sp)) <= TOL
+    ctx.close()
+
+
 def test_kuhn_box_full_size_properties(vt):
-    """At a size the oracle cannot hold (32^3 grid): size-independent properties — a uniform
+    """At the bench grid (32^3), on top of the comparison above: size-independent properties — a uniform
     state is a fixed point of transport, particles are conserved, and the step commutes with
     scaling (linearity)."""
     from vlasovtucker_b200 import synthetic
@@ -307,7 +341,6 @@ def test_kuhn_box_full_size_properties(vt):
     ctx.mesh_upload(mt)
     g = ctx.species_create(n, vmin, vmax, 1.0, 1.0)
     ctx.set_face_bc(g, np.full((mt.nTets, 4), vt.PBC["Periodic"], np.uint8))
-    ctx.step_config(chunk_planes=4)
     ax = np.linspace(-6, 6, 32)
     V0, V1, V2 = np.meshgrid(ax, ax, ax, indexing="ij")
     maxw = np.exp(-(V0 ** 2 + V1 ** 2 + V2 ** 2) / 2).ravel(order="F")

@@ -45,6 +45,7 @@ SIGNATURES = {
     "vt_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "vt_halo_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vt_halo_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_ip, C.c_void_p]),
+    "vt_halo_attach_local": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_ip, C.POINTER(C.c_void_p), c_ip]),
     "vt_halo_set_push": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_ip]),
     "vt_halo_push_current": (C.c_int, [C.c_void_p, C.c_int]),
     "vt_halo_barrier": (C.c_int, [C.c_void_p]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "vt_step_tucker": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
     "vt_tucker_halo_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vt_tucker_halo_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vt_tucker_halo_attach_local": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_ip]),
 }
 
 

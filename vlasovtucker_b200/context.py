@@ -198,6 +198,13 @@ class Context:
         ph = np.ascontiguousarray(peer_handles, np.uint8).reshape(len(pr), self.HALO_HANDLE_BYTES)
         capi.check(self.lib.vt_halo_attach(self.h, sp, int(my_rank), len(pr), capi.ip(pr), ph.ctypes.data_as(C.c_void_p)))
 
+    def halo_attach_local(self, sp, my_rank, peer_ranks, peer_ctxs, peer_species):
+        """In-process peers (virtual ranks on one device, or peer-accessible devices): no CUDA IPC."""
+        pr = capi.i32(peer_ranks)
+        arr = (C.c_void_p * len(pr))(*[c.h for c in peer_ctxs])
+        ps = capi.i32(peer_species)
+        capi.check(self.lib.vt_halo_attach_local(self.h, sp, int(my_rank), len(pr), capi.ip(pr), arr, capi.ip(ps)))
+
     def halo_set_push(self, sp, push_peer, push_row):
         pp = capi.i32(push_peer).reshape(self.nOwned, 4)
         pr = capi.i32(push_row).reshape(self.nOwned, 4)
@@ -290,6 +297,11 @@ class Context:
     def tucker_halo_attach(self, sp, peer_handles):
         h = np.ascontiguousarray(peer_handles, np.uint8).reshape(-1, self.TUCKER_HALO_HANDLE_BYTES)
         capi.check(self.lib.vt_tucker_halo_attach(self.h, sp, len(h), h.ctypes.data_as(C.c_void_p)))
+
+    def tucker_halo_attach_local(self, sp, peer_ctxs, peer_species):
+        arr = (C.c_void_p * len(peer_ctxs))(*[c.h for c in peer_ctxs])
+        ps = capi.i32(peer_species)
+        capi.check(self.lib.vt_tucker_halo_attach_local(self.h, sp, len(peer_ctxs), arr, capi.ip(ps)))
 
     def step_tucker(self, sp, dt, ext=(0.0, 0.0, 0.0)):
         ext = capi.f64(ext)

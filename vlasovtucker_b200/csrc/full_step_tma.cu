@@ -603,7 +603,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
 // NBD = 0: the producer bulk-copies whole neighbour planes; NBD = 2 or 4: the consumers request the
 // neighbour values they use themselves, NBD-1 planes ahead (upwind-select arithmetic only).
 template <int KPT, bool UPWIND, int NCW, bool ALLFAST, int SN, int NBD>
-__global__ void __maxnreg__(NCW == 8 ? 224 : 112) k_full_step_bulk(const BulkParams P)
+__global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkParams P)
 {
     static_assert(NBD == 0 || UPWIND, "consumer-side neighbour loads rely on the upwind select");
     const StepParams& p = P.s;

@@ -54,6 +54,30 @@ vt::Species& species_of(vt_ctx* ctx, int s)
     return *ctx->species[s];
 }
 
+void ensure_flags(vt_ctx* ctx)
+{
+    if (ctx->flags) return;
+    VT_CUDA(cudaMalloc(&ctx->flags, 64 * sizeof(uint32_t)));
+    VT_CUDA(cudaMemset(ctx->flags, 0, 64 * sizeof(uint32_t)));
+    VT_CUDA(cudaMalloc(&ctx->haloStatus, sizeof(int)));
+    VT_CUDA(cudaMemset(ctx->haloStatus, 0, sizeof(int)));
+}
+
+// the barrier kernel reads the peers' flag pointers and ranks from a small device table
+void upload_halo_table(vt_ctx* ctx)
+{
+    struct Table {
+        uint32_t* pf[vt::kMaxPeers];
+        int pr[vt::kMaxPeers];
+    } tb;
+    for (int i = 0; i < vt::kMaxPeers; i++) {
+        tb.pf[i] = ctx->peerFlags[i];
+        tb.pr[i] = ctx->peerRank[i];
+    }
+    if (!ctx->haloTable) VT_CUDA(cudaMalloc(&ctx->haloTable, sizeof(Table)));
+    VT_CUDA(cudaMemcpy(ctx->haloTable, &tb, sizeof(tb), cudaMemcpyHostToDevice));
+}
+
 template <class F>
 int guard(F f)
 {
@@ -79,12 +103,7 @@ int vt_halo_export(vt_ctx* ctx, int species, void* handles)
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
-        if (!ctx->flags) {
-            VT_CUDA(cudaMalloc(&ctx->flags, 64 * sizeof(uint32_t)));
-            VT_CUDA(cudaMemset(ctx->flags, 0, 64 * sizeof(uint32_t)));
-            VT_CUDA(cudaMalloc(&ctx->haloStatus, sizeof(int)));
-            VT_CUDA(cudaMemset(ctx->haloStatus, 0, sizeof(int)));
-        }
+        ensure_flags(ctx);
         IpcPack pk;
         VT_CUDA(cudaIpcGetMemHandle(&pk.f0, sp.f[0]));
         VT_CUDA(cudaIpcGetMemHandle(&pk.f1, sp.f[1]));
@@ -120,6 +139,45 @@ int vt_halo_attach(vt_ctx* ctx, int species, int myRank, int nPeers, const int32
                 ctx->ipcOpened.push_back(pf);
             }
         }
+        upload_halo_table(ctx);
+    });
+}
+
+int vt_halo_attach_local(vt_ctx* ctx, int species, int myRank, int nPeers, const int32_t* peerRanks,
+                         vt_ctx* const* peerCtx, const int32_t* peerSpecies)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        vt::Species& sp = species_of(ctx, species);
+        if (nPeers > vt::kMaxPeers) throw std::runtime_error("too many halo peers");
+        if (myRank < 0 || myRank >= 64) throw std::runtime_error("rank out of range for the barrier flags");
+        ensure_flags(ctx);
+        ctx->rank = myRank;
+        ctx->nPeers = nPeers;
+        sp.nPeers = nPeers;
+        for (int i = 0; i < nPeers; i++) {
+            if (peerRanks[i] < 0 || peerRanks[i] >= 64) throw std::runtime_error("peer rank out of range");
+            vt_ctx* pc = peerCtx[i];
+            if (!pc || pc == ctx) throw std::invalid_argument("vt_halo_attach_local: bad peer context");
+            vt::Species& psp = species_of(pc, peerSpecies[i]);
+            if (psp.N != sp.N) throw std::invalid_argument("vt_halo_attach_local: peer species has another velocity grid");
+            if (pc->device != ctx->device) {
+                int can = 0;
+                VT_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, pc->device));
+                if (!can) throw std::runtime_error("vt_halo_attach_local: no peer access between the devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(pc->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) VT_CUDA(e);
+                (void)cudaGetLastError();
+            }
+            VT_CUDA(cudaSetDevice(pc->device));
+            ensure_flags(pc);
+            VT_CUDA(cudaSetDevice(ctx->device));
+            ctx->peerRank[i] = peerRanks[i];
+            sp.peerF[i][0] = psp.f[0];
+            sp.peerF[i][1] = psp.f[1];
+            ctx->peerFlags[i] = pc->flags;
+        }
+        upload_halo_table(ctx);
     });
 }
 
@@ -164,23 +222,11 @@ int vt_halo_barrier(vt_ctx* ctx)
         VT_CUDA(cudaSetDevice(ctx->device));
         if (ctx->nPeers == 0) return;
         ctx->epoch++;
-        // kernel arguments: peer flag pointers and ranks live in a small device table
-        struct Table {
-            uint32_t* pf[vt::kMaxPeers];
-            int pr[vt::kMaxPeers];
-        } tb;
-        for (int i = 0; i < vt::kMaxPeers; i++) {
-            tb.pf[i] = ctx->peerFlags[i];
-            tb.pr[i] = ctx->peerRank[i];
-        }
-        // a dedicated tiny allocation owned by the context (the stage buffer may be in use)
-        if (!ctx->haloTable) {
-            VT_CUDA(cudaMalloc(&ctx->haloTable, sizeof(Table)));
-            VT_CUDA(cudaMemcpy(ctx->haloTable, &tb, sizeof(tb), cudaMemcpyHostToDevice));
-        }
-        Table* tableDev = static_cast<Table*>(ctx->haloTable);
-        uint32_t* const* pfDev = reinterpret_cast<uint32_t* const*>(tableDev);
-        const int* prDev = reinterpret_cast<const int*>(reinterpret_cast<const char*>(tableDev) + sizeof(tb.pf));
+        // peer flag pointers and ranks: the device table written by vt_halo_attach(_local)
+        if (!ctx->haloTable) upload_halo_table(ctx);
+        uint32_t* const* pfDev = reinterpret_cast<uint32_t* const*>(ctx->haloTable);
+        const int* prDev = reinterpret_cast<const int*>(reinterpret_cast<const char*>(ctx->haloTable) +
+                                                        vt::kMaxPeers * sizeof(uint32_t*));
         k_halo_barrier<<<1, 32, 0, ctx->stream>>>(ctx->flags, pfDev, prDev, ctx->nPeers, ctx->rank, ctx->epoch,
                                                   ctx->haloStatus);
         ctx->launches++;

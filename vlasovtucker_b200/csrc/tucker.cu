@@ -1111,6 +1111,22 @@ int vt_tucker_halo_attach(vt_ctx* ctx, int species, int nPeers, const void* peer
     });
 }
 
+int vt_tucker_halo_attach_local(vt_ctx* ctx, int species, int nPeers, vt_ctx* const* peerCtx, const int32_t* peerSpecies)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        Species& sp = species_of(ctx, species);
+        TuckerState& ts = state_of(sp);
+        if (nPeers != sp.nPeers) throw std::runtime_error("vt_tucker_halo_attach_local: call vt_halo_attach_local with the same peers first");
+        for (int i = 0; i < nPeers; i++) {
+            TuckerState& ps = state_of(species_of(peerCtx[i], peerSpecies[i]));
+            if (ps.slot != ts.slot) throw std::runtime_error("peer Tucker state has a different slot size (maxRank / grid mismatch)");
+            tucker_block_pointers(ps.block, ps.rows, ps.slot, ts.peerBuf[i], ts.peerRanks[i]);
+        }
+        ts.nPeers = nPeers;
+    });
+}
+
 int vt_tucker_set_pdf(vt_ctx* ctx, int species, const double* dense)
 {
     // vt_species_set_pdf re-compresses a Tucker species after the upload

@@ -43,6 +43,89 @@ class PartitionedSpecies:
         self.ctx.sync()
 
 
+class VirtualRanks:
+    """All ranks of a partitioned mesh inside ONE process: one context per rank, on the devices given
+    (the same device for every rank = "virtual ranks"), ghost rows wired directly
+    to the peers' buffers (vt_halo_attach_local).  Exactly the kernels, push lists and device-side
+    barrier of the one-process-per-GPU run; only the handle exchange differs.  A box with a single
+    GPU can therefore check the halo path."""
+
+    def __init__(self, tables, owner, world, devices=None, order=None):
+        devices = [0] * world if devices is None else list(devices)
+        self.world = world
+        owner = np.asarray(owner)
+        self.owner = owner
+        self.lps = [part.partition(tables, owner, r, None if order is None else np.asarray(order)[owner[np.asarray(order)] == r])
+                    for r in range(world)]
+        self.ctxs = [Context(devices[r]) for r in range(world)]
+        for ctx, lp in zip(self.ctxs, self.lps):
+            ctx.mesh_upload(lp.tables)
+        self.nGlobal = tables.nTets
+
+    def species_create(self, n, vmin, vmax, mass, charge, bc_type=None, collect=None, tucker=None):
+        """One species on every rank; bc_type/collect are global (nTets, 4) arrays.  Returns the
+        per-rank species ids (equal on all ranks when the calls are made in the same order)."""
+        ids = []
+        for ctx, lp in zip(self.ctxs, self.lps):
+            sp = ctx.species_create(n, vmin, vmax, mass, charge)
+            nO = len(lp.owned)
+            bc = np.full((nO, 4), PBC["Periodic"], np.uint8) if bc_type is None else bc_type[lp.owned]
+            ctx.set_face_bc(sp, bc, None if collect is None else collect[lp.owned])
+            ids.append(sp)
+        for r, (ctx, lp) in enumerate(zip(self.ctxs, self.lps)):
+            if lp.peers:
+                ctx.halo_attach_local(ids[r], r, lp.peers, [self.ctxs[q] for q in lp.peers], [ids[q] for q in lp.peers])
+                ctx.halo_set_push(ids[r], lp.push_peer, lp.push_row)
+        if tucker is not None:
+            for r, ctx in enumerate(self.ctxs):
+                ctx.tucker_enable(ids[r], tucker[0], tucker[1])
+            for r, (ctx, lp) in enumerate(zip(self.ctxs, self.lps)):
+                if lp.peers:
+                    ctx.tucker_halo_attach_local(ids[r], [self.ctxs[q] for q in lp.peers], [ids[q] for q in lp.peers])
+        return ids
+
+    def scatter(self, a):
+        """Global per-tet array -> list of per-rank owned slices."""
+        return [np.ascontiguousarray(a[lp.owned]) for lp in self.lps]
+
+    def gather(self, parts):
+        out = np.zeros((self.nGlobal,) + parts[0].shape[1:], parts[0].dtype)
+        for lp, p in zip(self.lps, parts):
+            out[lp.owned] = p
+        return out
+
+    def fill_ghosts(self, ids):
+        for r, ctx in enumerate(self.ctxs):
+            ctx.halo_push_current(ids[r])
+        self.barrier()
+        self.sync()
+
+    def barrier(self):
+        """Every rank's device-side barrier, queued on its own stream (they wait for each other on
+        the device, not on the host)."""
+        for ctx, lp in zip(self.ctxs, self.lps):
+            ctx.halo_barrier()
+
+    def sync(self):
+        for ctx in self.ctxs:
+            ctx.sync()
+
+    def step_full(self, ids, dt, ext=(0.0, 0.0, 0.0)):
+        for r, ctx in enumerate(self.ctxs):
+            ctx.step_full(ids[r], dt, ext)
+        self.barrier()
+
+    def step_tucker(self, ids, dt, ext=(0.0, 0.0, 0.0)):
+        for r, ctx in enumerate(self.ctxs):
+            ctx.step_tucker(ids[r], dt, ext)
+        self.barrier()
+
+    def close(self):
+        self.sync()
+        for ctx in self.ctxs:
+            ctx.close()
+
+
 class WeakScaledBox:
     """Config C4 weak scaling: every rank owns one block of `hexes` Kuhn hexes of a periodic box
     that is `rank_grid(world)` blocks large."""
