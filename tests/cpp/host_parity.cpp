@@ -24,6 +24,71 @@ static void DumpState(ofstream& out, const Mesh& mesh, PD& pd)
     out.write((const char*)vel.data(), vel.size() * sizeof(Vector3d));
 }
 
+// examples/sheath.cpp, shortened; TensorType is the alias the example flips (sheath.cpp:10)
+template <typename TensorType>
+static void RunSheath(const string& meshFile, int iterations, ofstream& out, int n0)
+{
+    double elTemperature = 1 * electronvolt, ionTemperature = 400, density = 1e17, ionMass = atomicMass;
+    double debyeLength = DebyeLength(elTemperature, density, elCharge);
+    double plasmaT = 2 * pi / PlasmaFrequency(density, elCharge, elMass);
+    Mesh mesh(meshFile);
+    mesh.SetPeriodicBounaries({{3, 4}, {5, 6}});
+    mesh.Reconstruct(22 * debyeLength);
+    double maxVE = sqrt(-log(1e-6) * 2 * boltzConst * elTemperature / elMass);
+    VelocityGrid vGridE({n0, 5, 5}, {-4 * maxVE, -maxVE, -maxVE}, {4 * maxVE, maxVE, maxVE});
+    double maxVI = sqrt(-log(1e-6) * 2 * boltzConst * ionTemperature / ionMass);
+    VelocityGrid vGridI({n0, 5, 5}, {-4 * maxVI, -maxVI, -maxVI}, {4 * maxVI, maxVI, maxVI});
+    auto rhoFunc = [density](const Point&) { return density; };
+    ParticleData<TensorType> particleDataE(&mesh, &vGridE);
+    particleDataE.species = "electron";
+    particleDataE.mass = elMass;
+    particleDataE.charge = -elCharge;
+    particleDataE.SetCompressionError(1e-6);
+    MaxwellPDF maxwellE;
+    maxwellE.physDensity = ScalarField(&mesh, rhoFunc);
+    maxwellE.temperature = elTemperature;
+    maxwellE.mostProbableV = {0, 0, 0};
+    particleDataE.SetMaxwellPDF(maxwellE);
+    ParticleData<TensorType> particleDataI(&mesh, &vGridI);
+    particleDataI.species = "ion";
+    particleDataI.mass = ionMass;
+    particleDataI.charge = elCharge;
+    particleDataI.SetCompressionError(1e-6);
+    MaxwellPDF maxwellI;
+    maxwellI.physDensity = ScalarField(&mesh, rhoFunc);
+    maxwellI.temperature = ionTemperature;
+    maxwellI.mostProbableV = {0, 0, 0};
+    particleDataI.SetMaxwellPDF(maxwellI);
+    Solver<TensorType> solverE(&mesh, &vGridE, &particleDataE);
+    Solver<TensorType> solverI(&mesh, &vGridI, &particleDataI);
+    ParticleBC<TensorType> particleBC1;
+    particleBC1.type = ParticleBCType::Absorbing;
+    particleBC1.collectCharge = true;
+    solverE.SetParticleBC(1, particleBC1);
+    solverI.SetParticleBC(1, particleBC1);
+    ParticleBC<TensorType> particleBC2;
+    particleBC2.type = ParticleBCType::Free;
+    solverE.SetParticleBC(2, particleBC2);
+    solverI.SetParticleBC(2, particleBC2);
+    FieldBC fieldBC1;
+    fieldBC1.type = FieldBCType::ChargedPlane;
+    fieldBC1.chargeDensity = 0;
+    solverE.SetFieldBC(1, fieldBC1);
+    FieldBC fieldBC2;
+    fieldBC2.type = FieldBCType::ConstantPotential;
+    fieldBC2.potential = 0;
+    solverE.SetFieldBC(2, fieldBC2);
+    MulticomponentSolver<TensorType> multiSolver(&solverE);
+    multiSolver.AddSolver(&solverI);
+    multiSolver.timeStep = 1e-4 * plasmaT;
+    multiSolver.stepMultipliers[&solverI] = 10;
+    multiSolver.stepMultipliers[&solverE] = 1;
+    multiSolver.nIterations = iterations;
+    multiSolver.Solve();
+    DumpState(out, mesh, particleDataE);
+    DumpState(out, mesh, particleDataI);
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 5) {
@@ -127,64 +192,10 @@ int main(int argc, char** argv)
         solver.Solve();
         DumpState(out, mesh, particleData);
     } else if (which == "sheath") {
-        // examples/sheath.cpp, shortened
-        double elTemperature = 1 * electronvolt, ionTemperature = 400, density = 1e17, ionMass = atomicMass;
-        double debyeLength = DebyeLength(elTemperature, density, elCharge);
-        double plasmaT = 2 * pi / PlasmaFrequency(density, elCharge, elMass);
-        Mesh mesh(meshFile);
-        mesh.SetPeriodicBounaries({{3, 4}, {5, 6}});
-        mesh.Reconstruct(22 * debyeLength);
-        double maxVE = sqrt(-log(1e-6) * 2 * boltzConst * elTemperature / elMass);
-        VelocityGrid vGridE({50, 5, 5}, {-4 * maxVE, -maxVE, -maxVE}, {4 * maxVE, maxVE, maxVE});
-        double maxVI = sqrt(-log(1e-6) * 2 * boltzConst * ionTemperature / ionMass);
-        VelocityGrid vGridI({50, 5, 5}, {-4 * maxVI, -maxVI, -maxVI}, {4 * maxVI, maxVI, maxVI});
-        auto rhoFunc = [density](const Point&) { return density; };
-        ParticleData<Full> particleDataE(&mesh, &vGridE);
-        particleDataE.species = "electron";
-        particleDataE.mass = elMass;
-        particleDataE.charge = -elCharge;
-        MaxwellPDF maxwellE;
-        maxwellE.physDensity = ScalarField(&mesh, rhoFunc);
-        maxwellE.temperature = elTemperature;
-        maxwellE.mostProbableV = {0, 0, 0};
-        particleDataE.SetMaxwellPDF(maxwellE);
-        ParticleData<Full> particleDataI(&mesh, &vGridI);
-        particleDataI.species = "ion";
-        particleDataI.mass = ionMass;
-        particleDataI.charge = elCharge;
-        MaxwellPDF maxwellI;
-        maxwellI.physDensity = ScalarField(&mesh, rhoFunc);
-        maxwellI.temperature = ionTemperature;
-        maxwellI.mostProbableV = {0, 0, 0};
-        particleDataI.SetMaxwellPDF(maxwellI);
-        Solver<Full> solverE(&mesh, &vGridE, &particleDataE);
-        Solver<Full> solverI(&mesh, &vGridI, &particleDataI);
-        ParticleBC<Full> particleBC1;
-        particleBC1.type = ParticleBCType::Absorbing;
-        particleBC1.collectCharge = true;
-        solverE.SetParticleBC(1, particleBC1);
-        solverI.SetParticleBC(1, particleBC1);
-        ParticleBC<Full> particleBC2;
-        particleBC2.type = ParticleBCType::Free;
-        solverE.SetParticleBC(2, particleBC2);
-        solverI.SetParticleBC(2, particleBC2);
-        FieldBC fieldBC1;
-        fieldBC1.type = FieldBCType::ChargedPlane;
-        fieldBC1.chargeDensity = 0;
-        solverE.SetFieldBC(1, fieldBC1);
-        FieldBC fieldBC2;
-        fieldBC2.type = FieldBCType::ConstantPotential;
-        fieldBC2.potential = 0;
-        solverE.SetFieldBC(2, fieldBC2);
-        MulticomponentSolver<Full> multiSolver(&solverE);
-        multiSolver.AddSolver(&solverI);
-        multiSolver.timeStep = 1e-4 * plasmaT;
-        multiSolver.stepMultipliers[&solverI] = 10;
-        multiSolver.stepMultipliers[&solverE] = 1;
-        multiSolver.nIterations = iterations;
-        multiSolver.Solve();
-        DumpState(out, mesh, particleDataE);
-        DumpState(out, mesh, particleDataI);
+        RunSheath<Full>(meshFile, iterations, out, 50);
+    } else if (which == "sheath_tucker") {
+        // the same driver with `using TensorType = Tucker;` (examples/sheath.cpp:10), smaller grid
+        RunSheath<Tucker>(meshFile, iterations, out, 20);
     } else {
         cerr << "unknown case\n";
         return 2;

@@ -32,7 +32,7 @@ def _split(buf, nT, N):
     return f, dens, vel, buf[nT * N + 4 * nT:]
 
 
-@pytest.mark.parametrize("mesh,iters", [("fully_periodic_coarse.msh", 25), ("rectangle.msh", 25)])
+@pytest.mark.parametrize("mesh,iters", [("fully_periodic_coarse.msh", 25), ("rectangle.msh", 25), ("rectangle_fine.msh", 200)])
 def test_oscillations_driver(oracle_mod, tmp_path, mesh, iters):
     m = oracle_mod.Mesh.load(mesh_path(mesh), [(1, 2), (3, 4), (5, 6)])
     buf = _run("oscillations", mesh, iters, tmp_path)
@@ -88,7 +88,7 @@ def test_sheath_driver(oracle_mod, tmp_path):
     debye = np.sqrt(EPS0 * kB * Te / dens0) / e
     wp = e * np.sqrt(dens0 / (me * EPS0))
     dt = 1e-4 * (2 * PI / wp)
-    iters = 21
+    iters = 200   # C3 of SURVEY.md §8d
     m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(3, 4), (5, 6)], scale=22 * debye)
     buf = _run("sheath", "rectangle_fine.msh", iters, tmp_path)
     fe, de, ve, rest = _split(buf, m.nTets, 1250)
@@ -112,6 +112,56 @@ def test_sheath_driver(oracle_mod, tmp_path):
     assert rel_l2(fi, s.get_pdf(1)) <= 1e-10
     assert rel_l2(de, s.density(0)) <= 1e-10
     assert rel_l2(di, s.density(1)) <= 1e-10
+
+
+def test_sheath_driver_tucker(oracle_mod, tmp_path):
+    """examples/sheath.cpp with `using TensorType = Tucker;`: MulticomponentSolver<Tucker>::Solve runs the
+    whole loop (shared Poisson solve, ion sub-cycling, merged wall charge -> Neumann BC) on the device
+    Tucker path; checked against the oracle's Tucker algebra + Poisson solver driven in the loop order of
+    multicomponent_solver.cpp:55-126."""
+    kB, e, me, mi, eV = 1.38e-23, 1.6e-19, 9.1e-31, 1.66e-27, 11604.518
+    Te, Ti, dens0, eps = 1 * eV, 400.0, 1e17, 1e-6
+    debye = np.sqrt(EPS0 * kB * Te / dens0) / e
+    wp = e * np.sqrt(dens0 / (me * EPS0))
+    dt = 1e-4 * (2 * PI / wp)
+    iters, n = 12, (20, 5, 5)
+    N = n[0] * n[1] * n[2]
+    m = oracle_mod.Mesh.load(mesh_path("rectangle.msh"), [(3, 4), (5, 6)], scale=22 * debye)
+    buf = _run("sheath_tucker", "rectangle.msh", iters, tmp_path)
+    fe, de, ve, rest = _split(buf, m.nTets, N)
+    fi, di, vi, rest = _split(rest, m.nTets, N)
+    assert rest.size == 0
+    maxVE = np.sqrt(-np.log(1e-6) * 2 * kB * Te / me)
+    maxVI = np.sqrt(-np.log(1e-6) * 2 * kB * Ti / mi)
+    sims, mults = [], [1, 10]
+    init = oracle_mod.Sim(m)    # the Full-format oracle tabulates the same Maxwellians (particle_data.cpp:23-90)
+    for k, (vmax, mass, q, T) in enumerate([(maxVE, me, -e, Te), (maxVI, mi, e, Ti)]):
+        vmin_, vmax_ = [-4 * vmax, -vmax, -vmax], [4 * vmax, vmax, vmax]
+        sp = init.add_species(n, vmin_, vmax_, mass, q)
+        init.set_maxwell(sp, np.full(m.nTets, dens0), T)
+        ts = oracle_mod.TuckerSim(m, n, vmin_, vmax_, mass, q, eps)
+        ts.set_pdf(init.get_pdf(sp))
+        ts.set_particle_bc(1, "Absorbing", True)
+        ts.set_particle_bc(2, "Free", False)
+        sims.append((ts, q))
+    area = float(m.faceArea[m.faceEntity == 1].sum())
+    po = oracle_mod.Poisson(m)
+    po.set_bc(1, "Neumann", 0.0, 0.0)
+    po.set_bc(2, "Dirichlet", 0.0, 0.0)
+    po.initialize()
+    for it in range(iters):
+        rho = sum(q * ts.density() for ts, q in sims)
+        _, E = po.solve(rho)
+        for (ts, q), mult in zip(sims, mults):
+            if it % mult == 0:
+                ts.update_pdf(dt * mult, E)
+        Q = sum(ts.wall_charge(1) for ts, _ in sims)
+        po.set_bc(1, "Neumann", 0.0, (Q / area) / (2 * EPS0))
+    tol = eps + 1e-10
+    assert rel_l2(fe, sims[0][0].get_pdf()) <= tol
+    assert rel_l2(fi, sims[1][0].get_pdf()) <= tol
+    assert rel_l2(de, sims[0][0].density()) <= tol
+    assert rel_l2(di, sims[1][0].density()) <= tol
 
 
 @pytest.mark.parametrize("case,tol", [("snapshot", 0.0), ("snapshot_tucker", 1e-8)])

@@ -158,7 +158,8 @@ def _coupled_single(vt, oracle_mod, mesh, steps, q, n=(11, 11, 11)):
     return m, s, sp, ctx, g
 
 
-@pytest.mark.parametrize("mesh,steps", [("fully_periodic_coarse.msh", 30), ("rectangle.msh", 30)])
+# C1s of SURVEY.md §8d is rectangle_fine.msh for N = 200 iterations
+@pytest.mark.parametrize("mesh,steps", [("fully_periodic_coarse.msh", 30), ("rectangle.msh", 30), ("rectangle_fine.msh", 200)])
 def test_coupled_loop_parity(vt, oracle_mod, mesh, steps):
     m, s, sp, ctx, g = _coupled_single(vt, oracle_mod, mesh, steps, 2.975e-5)
     rho_o, phi_o, E_o = s.fields(sp)
@@ -233,7 +234,7 @@ def test_sheath_two_species_loop(vt, oracle_mod):
     qb, val, ng = poisson_bc_arrays(m, spec)
     ctx.poisson_setup(qb, val, ng)
     area = s.wall_area(0, 1)
-    steps = 21
+    steps = 200   # C3 of SURVEY.md §8d: N = 200 iterations (the ions take 20 sub-cycled steps)
     for it in range(steps):
         s.step(it)
         ctx.charge_density([g for g, _ in gs])

@@ -500,7 +500,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
         for (int f = 0; f < 4; f++) tzf[f] = __dmul_rn(cz[f], v2);
 #pragma unroll
         for (int kk = 0; kk < KPT; kk++) {
-            if (!col[kk].on) continue;
+            if (!PAIRED && !col[kk].on) continue;   // the paired layout covers the plane exactly
             const double2 nx = lds128(snA + oEv[kk]);
             nv[kk] = nx;
             // PAIRED: the thread's two columns are neighbours in i1, so each one's i1 neighbour on
@@ -602,8 +602,21 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
 
 // NBD = 0: the producer bulk-copies whole neighbour planes; NBD = 2 or 4: the consumers request the
 // neighbour values they use themselves, NBD-1 planes ahead (upwind-select arithmetic only).
+// Register budget: the CTA is NCW consumer warps plus one auxiliary warp GROUP (four warps, of which
+// one lane runs the producer).  A separate producer WARP would make 9 (17) warps, i.e. three (five)
+// on one SM sub-partition, and cap every thread at 168 (96) registers; with whole warp groups the
+// auxiliary group hands its registers back (setmaxnreg.dec) and the consumer groups take them
+// (setmaxnreg.inc): 232 registers per consumer thread with eight consumer warps, 104 with sixteen (RegSplit).
+constexpr int kAuxThreads = 128;
+// registers after the reallocation; 4 * aux + NCW * consumer <= (NCW + 4) * launch count (168 / 96)
+template <int NCW, int NBD>
+struct RegSplit {
+    static constexpr int aux = (NCW == 8 && NBD > 0) ? 40 : 56;   // the producer that also copies neighbour planes needs more
+    static constexpr int consumer = NCW == 8 ? (NBD > 0 ? 232 : 224) : 104;
+};
+
 template <int KPT, bool UPWIND, int NCW, bool ALLFAST, int SN, int NBD>
-__global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkParams P)
+__global__ void __launch_bounds__(NCW * 32 + kAuxThreads, 1) k_full_step_bulk(const BulkParams P)
 {
     static_assert(NBD == 0 || UPWIND, "consumer-side neighbour loads rely on the upwind select");
     const StepParams& p = P.s;
@@ -640,9 +653,11 @@ __global__ void __launch_bounds__(NCW * 32 + 32, 1) k_full_step_bulk(const BulkP
     __syncthreads();
 
     if (tid >= NCW * 32) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RegSplit<NCW, NBD>::aux));
         if (tid == NCW * 32) producer_loop<(NBD > 0)>(P, sm);
         return;
     }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RegSplit<NCW, NBD>::consumer));
 
     // fixed columns of this consumer thread
     constexpr bool SPEC = SN > 0 && KPT == 2 && NCW == 8;
@@ -719,7 +734,7 @@ void launch_cfg(vt_ctx* ctx, const BulkParams& P, bool upwind, bool allFast, siz
     auto launch = [&](auto kern) {
         VT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         VT_CUDA(cudaMemsetAsync(P.queue, 0, sizeof(unsigned long long), stream));
-        kern<<<grid, NCW * 32 + 32, smem, stream>>>(P);
+        kern<<<grid, NCW * 32 + kAuxThreads, smem, stream>>>(P);
         ctx->launches++;
     };
     if constexpr (NBD > 0) {

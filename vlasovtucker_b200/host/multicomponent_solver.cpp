@@ -22,10 +22,12 @@ void MulticomponentSolver<T>::AddSolver(Solver<T>* solver)
     _solvers.push_back(solver);
 }
 
-template <>
-void MulticomponentSolver<Full>::Solve()
+// One body for both tensor formats: everything it calls (vt_charge_density, the device Poisson solve,
+// Solver<T>::_UpdatePDF, the wall-charge pull) is format-agnostic (multicomponent_solver.cpp:27-135).
+template <typename T>
+void MulticomponentSolver<T>::Solve()
 {
-    Solver<Full>* base = _solvers[0];
+    Solver<T>* base = _solvers[0];
     for (auto* s : _solvers)
         if (!stepMultipliers.count(s)) stepMultipliers[s] = 1;
     for (auto* s : _solvers) {
@@ -86,16 +88,12 @@ void MulticomponentSolver<Full>::Solve()
                 s->_rho = rho;
                 s->_phi = base->_poissonSolver.Potential();
                 s->_field = base->_poissonSolver.ElectricField();
+                s->_pData->SyncFromDevice();   // Tucker: the host mirror feeds the distribution dump
                 s->_WriteResults(iteration);
             }
         }
     }
-}
-
-template <>
-void MulticomponentSolver<Tucker>::Solve()
-{
-    _solvers[0]->_UpdatePDF();   // reports the missing device implementation
+    for (auto* s : _solvers) s->_pData->SyncFromDevice();
 }
 
 template class MulticomponentSolver<Full>;
