@@ -127,13 +127,15 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fused=False, keep=None):
+def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fused=False, keep=None, budget_s=12.0):
     """The oracle's reference-faithful restatement of _UpdatePDF (one temporary per tensor
-    operator, OpenMP over tets as src/solver.cpp:159,187,204) on a bounded sample of C4."""
+    operator, OpenMP over tets as src/solver.cpp:159,187,204) on a bounded sample of C4, timed with
+    whichever build of the oracle this process loaded (see cpu_baseline_native)."""
     threads = threads or os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(threads)
     import oracle
-    oracle.build()
+    if not os.environ.get("VT_ORACLE_SO"):
+        oracle.build()
     from vlasovtucker_b200 import synthetic
     cfg = c4_setup(hexes, nv)
     nodes, tets, tris, ents = synthetic.kuhn_box(*hexes, cfg["lengths"])
@@ -149,8 +151,8 @@ def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fus
     for _ in range(warmup):
         s.update_pdf(sp, E)
     tw = (time.perf_counter() - tw) / max(1, warmup)
-    if steps is None:   # bounded sample: about 12 s of CPU work
-        steps = int(min(40, max(2, round(12.0 / max(tw, 1e-3)))))
+    if steps is None:   # bounded sample
+        steps = int(min(40, max(2, round(budget_s / max(tw, 1e-3)))))
     t0 = time.perf_counter()
     for _ in range(steps):
         s.update_pdf(sp, E)
@@ -161,7 +163,49 @@ def cpu_baseline(steps=None, warmup=1, hexes=(8, 8, 8), nv=32, threads=None, fus
     return dict(value=updates / dt, unit="updates/s", cores=threads, kind="port",
                 sample=f"Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]}x6={m.nTets} tets x {nv}^3, "
                        f"{steps} timed _UpdatePDF steps ({'fused single-pass' if fused else 'reference-faithful temporaries'}, "
-                       f"OpenMP {threads} threads)", ms_per_step=dt * 1e3)
+                       f"OpenMP {threads} threads)", ms_per_step=dt * 1e3, steps=steps, warmup=warmup)
+
+
+def cpu_baseline_native(steps=None, warmup=1, budget_s=10.0):
+    """CPU numbers with the reference's own compiler flags (CMakeLists.txt:6: -O3 -fno-math-errno
+    -march=native, default contraction) — the oracle rebuilt ON THIS MACHINE (oracle/_native/) and timed
+    in a child process: the reference-faithful mode (the reference's allocation pattern) and the fused
+    single-pass mode (what a careful CPU implementation would do).  Returns None when that build is not
+    possible here (no compiler on the box); the caller then falls back to the portable checker build."""
+    try:
+        import oracle
+        so = oracle.build_native()
+    except Exception:
+        return None
+    out = {}
+    for mode in ("faithful", "fused"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", mode, "--warmup", str(warmup)]
+        if steps is not None:
+            cmd += ["--steps", str(steps)]
+        env = dict(os.environ, VT_ORACLE_SO=so, VT_CPU_BUDGET_S=str(budget_s if mode == "faithful" else budget_s / 2))
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        if r.returncode != 0:
+            return None
+        out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    return out
+
+
+def cpu_legs(steps=None, warmup=1, keep=None):
+    """cpu_baseline object of the bench line: the reference-flag build where it can be made, the
+    portable checker build (x86-64-v3, -ffp-contract=off: the one the parity tests use) beside it."""
+    native = cpu_baseline_native(steps=steps, warmup=warmup)
+    # the checker build also advances the parity sample (few steps: its job here is the end state)
+    port = cpu_baseline(steps=2 if native else steps, warmup=warmup, keep=keep)
+    if native is None:
+        cb = {k: port[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb["flags"] = "-O3 -fno-math-errno -march=x86-64-v3 -ffp-contract=off -fopenmp (portable checker build; native build unavailable)"
+        return cb, port
+    f, u = native["faithful"], native["fused"]
+    cb = {"value": f["value"], "unit": f["unit"], "cores": f["cores"], "kind": "port", "sample": f["sample"],
+          "flags": "-O3 -fno-math-errno -march=native -fopenmp (the reference's CMakeLists.txt:6 + OpenMP), built on this host",
+          "fused_cpu": {"value": u["value"], "sample": u["sample"]},
+          "portable_checker_build": {"value": port["value"], "flags": "-march=x86-64-v3 -ffp-contract=off", "sample": port["sample"]}}
+    return cb, f
 
 
 def parity_vs_oracle(keep, device, variant, chunk_planes):
@@ -206,16 +250,16 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    cb = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+    cb, timed = cpu_legs(steps=max(1, args.steps), warmup=max(1, args.warmup))
     line = {
         "impl": "reference", "metric": "cell x v-node updates/s per step (full format)", "value": cb["value"],
-        "unit": "updates/s", "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 1)),
-        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "unit": "updates/s", "n_gpus": args.gpus, "steps": timed["steps"], "warmup": timed["warmup"],
+        "ms_per_step": timed["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(tuple(args.hexes), args.nv),
                    "cpu_arm": "timed on a bounded sample of the workload (see cpu_baseline.sample)",
                    "note": "reference itself cannot be compiled here (vendored Eigen lacks Eigen/Core); this is the oracle's line-by-line restatement"},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -381,8 +425,8 @@ def run_gpu(args):
             line["coupled_loop"] = coupled
         if not args.no_cpu_baseline and world == 1:
             keep = {}
-            cb = cpu_baseline(keep=keep)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            cb, _ = cpu_legs(keep=keep)
+            line["cpu_baseline"] = cb
             try:
                 line["parity"] = parity_vs_oracle(keep, local, args.variant, args.chunk_planes)
             except Exception as exc:
@@ -410,7 +454,14 @@ def main():
                          "arithmetic for 32^3), 2 = register-staged kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-coupled", action="store_true", help="skip the coupled-loop (Poisson + step) measurement")
+    ap.add_argument("--cpu-worker", default=None, choices=["faithful", "fused"], help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_worker:     # child of cpu_baseline_native: time one mode with the library VT_ORACLE_SO names
+        explicit = any(a == "--steps" for a in sys.argv)
+        cb = cpu_baseline(steps=args.steps if explicit else None, warmup=max(1, args.warmup), fused=args.cpu_worker == "fused",
+                          budget_s=float(os.environ.get("VT_CPU_BUDGET_S", "10")))
+        print(json.dumps(cb), flush=True)
+        return
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":

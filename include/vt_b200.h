@@ -110,7 +110,7 @@ int vt_step_full_host(vt_ctx* ctx, int species, double dt, const double ext[3], 
  *      >= 4 KiB can be staged, register-staged kernel otherwise, upwind-select arithmetic);
  *    1 no warp shuffles, 2 upwind-select arithmetic (vn>0 ? vn*f : vn*fa instead of the reference's
  *      0.5*(vn*(fa+f) - |vn|*(fa-f)); equal up to rounding), 4 three resident CTAs per SM,
- *    8 persistent cp.async pipeline, 16 persistent bulk-copy (cp.async.bulk + mbarrier)
+ *    (8 unused,) 16 persistent bulk-copy (cp.async.bulk + mbarrier)
  *      producer/consumer pipeline, 32 with 16: eight consumer warps x two columns instead of sixteen;
  *  128 with 16|32|2: neighbour planes as whole-plane bulk copies instead of the consumer-side loads of
  *      only the inflow half of every neighbour row (the default where the eight-warp layout applies),

@@ -30,10 +30,16 @@ def build(force=False):
     return so
 
 
+def build_native():
+    """The timing build with the reference's flags (-march=native), made on the machine that runs it."""
+    subprocess.check_call(["make", "-C", _HERE, "_native/liboracle_native.so"], stdout=subprocess.DEVNULL)
+    return os.path.join(_HERE, "_native", "liboracle_native.so")
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        so = os.path.join(_HERE, "liboracle.so")
+        so = os.environ.get("VT_ORACLE_SO") or os.path.join(_HERE, "liboracle.so")   # bench.py's timing build
         if not os.path.exists(so):
             build()
         L = C.CDLL(so)

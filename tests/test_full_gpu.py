@@ -64,30 +64,21 @@ def _run_pair(vt, oracle_mod, m, n, vmin, vmax, mass, charge, f0, E, dt, steps, 
 
 
 @pytest.mark.parametrize("n,chunk,brick,variant", [
-    # variant bits: 1 no shuffles, 2 upwind-select arithmetic, 8 persistent cp.async pipeline,
-    # 16 persistent bulk-copy (TMA) pipeline; default = register-staged kernel, reference shape
+    # variant bits: 1 no shuffles, 2 upwind-select arithmetic, 16 persistent bulk-copy (TMA) pipeline, 32 eight
+    # consumer warps, 128 whole neighbour planes, 256 tet-major items; 0 = register-staged kernel, reference shape
     ((11, 11, 11), None, None, None),     # C1 grid: odd n0 -> scalar path
     ((11, 11, 11), 3, 100, 2),            # ragged chunks and bricks, upwind arithmetic
     ((8, 6, 4), None, None, None),        # double2 path without shuffles
     ((8, 6, 4), 3, 50, 2),
-    ((8, 6, 4), None, None, 8),           # cp.async pipeline, tiny planes (idle threads)
-    ((8, 6, 4), 3, 50, 10),               # cp.async, ragged chunk (4 planes in chunks of 3)
-    ((8, 6, 8), 1, 50, 10),               # cp.async, single-plane items (3 tickets per item)
     ((8, 6, 4), 3, 50, 18),               # TMA, ragged chunk
     ((16, 8, 8), None, None, None),       # shuffle path
     ((16, 8, 8), 2, 128, 1),              # shuffles disabled
     ((16, 8, 8), 2, 128, 2),              # upwind
-    ((16, 8, 8), None, None, 8),          # cp.async, whole tensor per work item
-    ((16, 8, 8), 2, 128, 10),             # cp.async, 2-plane chunks, upwind
-    ((16, 8, 8), 1, 128, 8),              # cp.async, single-plane chunks
     ((16, 8, 8), 2, 128, 16),             # TMA
     ((32, 4, 6), 3, 0, None),
     ((32, 32, 4), 2, 0, 2),               # the bench plane size
-    ((32, 32, 4), 2, 0, 10),              # cp.async at the bench plane size (2 columns per thread)
-    ((40, 40, 3), None, 0, 10),           # cp.async, 4 columns per thread
     ((48, 48, 3), None, 0, 18),           # TMA, 3 columns per thread
     ((50, 5, 5), None, None, None),       # sheath grid
-    ((50, 5, 5), None, None, 10),
     ((32, 32, 4), None, 0, None),         # library default at the bench plane size: bulk-copy pipeline, 8 warps x 2 columns
     ((32, 32, 4), 2, 0, 18),              # bulk-copy pipeline, 16 consumer warps, 2-plane items
     ((32, 32, 5), 1, 64, 50),             # single-plane items through the queue, bricks of 64 tets

@@ -330,7 +330,6 @@ __global__ void k_density_full(const double* __restrict__ f, double* __restrict_
 }  // namespace
 
 bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, cudaEvent_t e0, cudaEvent_t e1);
-bool launch_full_step_async(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, cudaEvent_t e0, cudaEvent_t e1);
 
 void launch_density(vt_ctx* ctx, Species& sp)
 {
@@ -440,14 +439,14 @@ void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3])
         VT_CUDA(cudaEventRecord(e1, ctx->stream));
     };
     // bit 4: the persistent bulk-copy (cp.async.bulk) producer/consumer pipeline — it counts its own
-    // launches (one, or two when boundary and interior tets are launched separately); bit 3: the
-    // persistent cp.async pipeline (opt-in).  Both fall through to the register-staged kernel where
-    // they do not apply.
+    // launches (one, or two when boundary and interior tets are launched separately).  Falls through
+    // to the register-staged kernel where it does not apply.  (Bit 3 selected a cp.async ring in round
+    // 1; it lost to the bulk-copy pipeline at every size and was removed.)
     bool useTma = false;
     if (ctx->variant & 16) {
         useTma = launch_full_step_tma(ctx, sp, p, upwind, e0, e1);
         if (useTma) ctx->launches--;   // compensates the increment below
-    } else if (ctx->variant & 8) useTma = launch_full_step_async(ctx, sp, p, upwind, e0, e1);
+    }
     // variant bit 2: ask the compiler for 3 resident CTAs per SM (<= 85 registers) instead of 2
     const bool dense = (ctx->variant & 4) != 0;
     if (useTma) {

@@ -15,10 +15,9 @@ Solver<T>::Solver(const Mesh* mesh, const VelocityGrid* vGrid, ParticleData<T>* 
     : _mesh(mesh), _vGrid(vGrid), _pData(pData), _poissonSolver(mesh)
 {
     _log = Log(LogLevel::Console);
-    // v.n and |v.n| are recomputed inside the step kernel; the reference stores 8 tensors per tet
-    // here (_PrecomputeNormalTensors) and reports their compression ratio
-    _log << "Normal speed size reduction: " << 1.0 << " times on average\n";
-    _log << "Absolute normal speed size reduction: " << 1.0 << " times on average\n";
+    // v.n and |v.n| are recomputed inside the step kernel; the reference stores 8 tensors per tet here
+    // (_PrecomputeNormalTensors, solver.cpp:258-293) and logs their compression ratio — there is no
+    // such tensor to report on, so nothing is logged
     _faceParticleBC.resize(mesh->faces.size());
     ParticleBC<T> periodic;
     periodic.type = ParticleBCType::Periodic;
