@@ -239,6 +239,246 @@ def parity_vs_oracle(keep, device, variant, chunk_planes):
                     f"({hexes[0]}x{hexes[1]}x{hexes[2]}x6 tets x {keep['nv']}^3), same initial condition and field"}
 
 
+# ---------------------------------------------------------------------------------------------------
+# Tucker format (config C5 of SURVEY.md §8d): per-cell Tucker update with rounding after every face,
+# after the acceleration term and after the Euler update (src/solver.cpp:141-212 with T = Tucker,
+# src/tucker.cpp:66-98).  value = cell x v-node updates/s as for the full format; the bounding roofline
+# is FP64: flops counted with the formula of SURVEY.md §8d for the reference's algorithm, divided by
+# the DFMA peak measured in the same run (vt_measure_dfma_peak).
+
+def c5_terms(nv, rank, vth):
+    """Velocity-space factors of `rank` shifted, anisotropic Maxwellians (multilinear rank = rank)."""
+    ax = np.linspace(-6 * vth, 6 * vth, nv)
+    k = np.arange(rank)
+    a = []
+    for j in range(3):
+        shift = vth * 1.5 * np.cos(2 * PI * (k + 0.37 * j) / max(rank, 1) + j)
+        width = vth * (0.8 + 0.35 * ((k + j) % 3))
+        a.append(np.exp(-0.5 * ((ax[None, :] - shift[:, None]) / width[:, None]) ** 2))
+    return a
+
+
+def c5_init(cfg, rank):
+    vth = np.sqrt(KB * cfg["T"] / EL_MASS)
+    a0, a1, a2 = c5_terms(cfg["n"][0], rank, vth)
+    norm = (a0.sum(1) * a1.sum(1) * a2.sum(1)) * np.prod([(12 * vth) / (cfg["n"][j] - 1) for j in range(3)])
+
+    def init(ctx, sp, x):
+        k = np.arange(rank)
+        amp = cfg["dens"] / rank * (1 + 0.01 * np.sin(2 * PI * x[:, None] + k[None, :])) / norm[None, :]
+        ctx.set_separable(sp, amp, a0, a1, a2)
+    return init
+
+
+def tucker_flops_survey(n, r, rmax):
+    """Flops of one tet-step of the REFERENCE's algorithm (six Compress calls, SURVEY.md §8d formula):
+    stacked ranks R = r_rhs + 16 r for the four faces, r_rhs + 3 r for the acceleration term, r + r_rhs
+    for the Euler update, R' = min(n, R), result rank r' = min(rmax, n)."""
+    rp = min(rmax, n)
+
+    def compress(R):
+        Rp = min(n, R)
+        qr = 3 * 2 * n * R * Rp
+        core = 3 * 2 * Rp ** 4
+        svd = 3 * (2 * Rp ** 4 + 12 * Rp ** 3)
+        proj = 2 * (Rp ** 3 * rp + Rp ** 2 * rp ** 2 + Rp * rp ** 3)
+        upd = 3 * 2 * n * Rp * rp
+        return qr + core + svd + proj + upd
+    total, rrhs = 0, 1
+    for _ in range(4):
+        total += compress(rrhs + 16 * r)
+        rrhs = rp
+    total += compress(rrhs + 3 * r)
+    total += compress(r + rrhs)
+    return float(total)
+
+
+def tucker_flops_executed(n):
+    """Flops of the dense formulation the device kernel executes per tet-step (csrc/tucker.cu): six
+    truncated HOSVDs of an n^3 tensor — three Gram matrices (n^4 FMA each) and three projections —
+    plus the reconstructions of the own, neighbour and |v.n| tensors (bounded by n^4 FMA each)."""
+    gram = 3 * 2 * n ** 4
+    proj = 3 * 2 * n ** 4          # upper bound: full-rank projection
+    return float(6 * (gram + proj) + 9 * 3 * 2 * n ** 4)
+
+
+def tucker_cpu_baseline(nv, rank, eps, hexes=(1, 1, 1), budget_s=20.0):
+    """The oracle's Tucker algebra (oracle/oracle_tucker.cpp: operator+, Hadamard product, QR + HOSVD
+    rounding as src/tucker.cpp) on a small Kuhn box with the C5 inputs, all host cores."""
+    threads = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    import oracle
+    oracle.build()
+    from vlasovtucker_b200 import synthetic
+    cfg = c4_setup(hexes, nv)
+    nodes, tets, tris, ents = synthetic.kuhn_box(*hexes, cfg["lengths"])
+    m = oracle.Mesh.from_arrays(nodes, tets, tris, ents, [(1, 2), (3, 4), (5, 6)])
+    vth = np.sqrt(KB * cfg["T"] / EL_MASS)
+    a0, a1, a2 = c5_terms(nv, rank, vth)
+    x = m.tetCentroid[:, 0] / cfg["lengths"][0]
+    k = np.arange(rank)
+    amp = cfg["dens"] / rank * (1 + 0.01 * np.sin(2 * PI * x[:, None] + k[None, :]))
+    f = np.einsum("tk,ka,kb,kc->tcba", amp, a0, a1, a2).reshape(m.nTets, -1)
+    ts = oracle.TuckerSim(m, cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"], eps, rank)
+    ts.set_pdf(f)
+    E = np.zeros((m.nTets, 3))
+    E[:, 0] = 1e3 * np.cos(2 * PI * x)
+    ts.update_pdf(cfg["dt"], E)      # untimed: the first call also tabulates v.n / |v.n| (solver.cpp:258-293, once per run)
+    t0 = time.perf_counter()
+    ts.update_pdf(cfg["dt"], E)
+    one = time.perf_counter() - t0
+    steps = int(min(10, max(1, round(budget_s / max(one, 1e-3)))))
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        ts.update_pdf(cfg["dt"], E)
+    per = (time.perf_counter() - t1) / steps
+    return dict(value=m.nTets * nv ** 3 / per, unit="updates/s", cores=threads, kind="port",
+                sample=f"Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]}x6={m.nTets} tets x {nv}^3, rank {rank}, eps {eps:g}: "
+                       f"{steps} timed Tucker _UpdatePDF steps of the oracle (real Tucker algebra, OpenMP {threads} threads)",
+                ms_per_step=per * 1e3)
+
+
+def tucker_cpu_worker_start(nv, rank_t, eps):
+    """The oracle's Tucker step costs ~40 core-seconds per tet at 48^3 — start it as a child process at
+    the beginning of the run (it uses 6 host cores while the GPU legs, which keep one core busy, run)
+    and collect the number at the end."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--tucker-cpu-worker", "--tucker-nv", str(nv),
+           "--tucker-rank", str(rank_t), "--tucker-eps", repr(eps)]
+    try:
+        return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return None
+
+
+def tucker_cpu_worker_collect(proc, timeout=600):
+    if proc is None:
+        return {"error": "could not start the CPU worker"}
+    try:
+        out, _ = proc.communicate(timeout=timeout)
+        cb = json.loads(out.strip().splitlines()[-1])
+        return {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    except Exception as exc:
+        try:
+            proc.kill()
+        except Exception:
+            pass
+        return {"error": str(exc)[:200]}
+
+
+def run_tucker(args, rank_world_local, dist, torch, hexes, nv, rank_t, eps, steps, warmup, cpu=True, cpu_proc=None):
+    """One Tucker measurement; returns the dict (rank 0) or None."""
+    rank, world, local = rank_world_local
+    import vlasovtucker_b200 as vtb
+    from vlasovtucker_b200 import synthetic
+    cfg = c4_setup(hexes, nv)
+    init = c5_init(cfg, rank_t)
+    brick = tuple(b if h % b == 0 else 1 for h, b in zip(hexes, (4, 4, 4)))
+    if world > 1:
+        from vlasovtucker_b200 import multigpu
+        runner = multigpu.WeakScaledBox(rank, world, local, hexes, cfg, brick=brick, dist=dist, tucker=(eps, rank_t), init=init)
+        ctx, sp, mt = runner.ctx, runner.sp, runner.mt
+        E = runner.E
+    else:
+        runner = None
+        ctx = vtb.Context(local)
+        mt = synthetic.periodic_kuhn_tables(*hexes, cfg["lengths"], brick=brick)
+        ctx.mesh_upload(mt)
+        sp = ctx.species_create(cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
+        ctx.set_face_bc(sp, np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8))
+        ctx.tucker_enable(sp, eps, rank_t)
+        x = mt.tetCentroid[:, 0] / cfg["lengths"][0]
+        init(ctx, sp, x)
+        E = np.zeros((mt.nTets, 3))
+        E[:, 0] = 1e3 * np.cos(2 * PI * x)
+        ctx.field_set(E)
+    nT, N, dt = mt.nTets, nv ** 3, cfg["dt"]
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step():
+        if runner is not None:
+            runner.step(dt)
+        else:
+            ctx.step_tucker(sp, dt)
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    ctx.profile_begin()
+    for _ in range(steps):
+        step()
+    region_ms, kern_ms, kern_n = ctx.profile_end()
+    launches = ctx.launch_count() - l0
+    barrier()
+    t_ms = region_ms
+    if dist is not None:
+        t = torch.tensor([region_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ms = float(t.item())
+    ms_per_step = t_ms / steps
+    ranks = ctx.tucker_ranks(sp)
+    # end to end: E from host memory in, Density() out to host memory, every step
+    if runner is not None:
+        e2e_ms = runner.e2e(dt, max(1, steps // 2), barrier) / max(1, steps // 2)
+    else:
+        ctx.field_set(E)
+        ctx.step_tucker(sp, dt)
+        ctx.tucker_density(sp)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps // 2)):
+            ctx.field_set(E)
+            ctx.step_tucker(sp, dt)
+            ctx.tucker_density(sp)
+        ctx.sync()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / max(1, steps // 2)
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    peak = ctx.dfma_peak_tflops()
+    if runner is not None:
+        runner.ctx.close()
+    else:
+        ctx.close()
+    if rank != 0:
+        return None
+    kern_avg = kern_ms / max(1, kern_n)
+    fl_ref = tucker_flops_survey(nv, rank_t, rank_t) * nT
+    fl_exe = tucker_flops_executed(nv) * nT
+    out = {
+        "metric": "cell x v-node updates/s per step (Tucker format)", "value": nT * N * world / (ms_per_step * 1e-3),
+        "unit": "updates/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5: periodic Kuhn box {hexes[0]}x{hexes[1]}x{hexes[2]} hexes x6 = {nT} tets/GPU x {nv}^3 velocity nodes, "
+                               f"Tucker format, f = sum of {rank_t} shifted anisotropic Maxwellians, SetMaxRank({rank_t}), comprErr {eps:g}",
+                   "tets_per_gpu": nT, "v_nodes": N, "max_rank": rank_t, "compr_err": eps,
+                   "mean_rank_after": float(ranks.mean()), "max_rank_after": int(ranks.max()),
+                   "tet_updates_per_s": nT * world / (ms_per_step * 1e-3)},
+        "roofline": {"bound": "fp64", "achieved": fl_ref / (kern_avg * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": fl_ref / (kern_avg * 1e-3) / 1e12 / peak, "traffic": None,
+                     "peak_source": "DFMA probe in this run (vt_measure_dfma_peak)", "kernel": "k_tucker", "kernel_ms": kern_avg,
+                     "flops_per_tet_step_counted": fl_ref / nT,
+                     "counted": "SURVEY.md §8d formula for the reference's six Compress calls (QR + core transform + 3 SVDs + projection)",
+                     "executed_flops_per_tet_step": fl_exe / nT, "executed_tflops": fl_exe / (kern_avg * 1e-3) / 1e12,
+                     "executed": "dense formulation of csrc/tucker.cu: 6 x (3 Gram matrices + 3 projections) + reconstructions",
+                     "kernel_share_of_step": kern_ms / region_ms},
+        "e2e": {"value": nT * N * world / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": 3 * nT * 8 * world,
+                "d2h_bytes_per_step": nT * 8 * world, "ms_per_step": e2e_ms,
+                "what": "vt_field_set (E from host) + vt_step_tucker + vt_tucker_density (to host); compressed state stays resident"},
+        "gpu_launches": int(launches),
+    }
+    if cpu and world == 1:
+        out["cpu_baseline"] = tucker_cpu_worker_collect(cpu_proc if cpu_proc is not None else tucker_cpu_worker_start(nv, rank_t, eps))
+    return out
+
+
 def workload_name(hexes, nv):
     """The workload both arms report (config.workload)."""
     nT = 6 * hexes[0] * hexes[1] * hexes[2]
@@ -282,6 +522,9 @@ def run_gpu(args):
     hexes = tuple(args.hexes)
     nv = args.nv
     cfg = c4_setup(hexes, nv)
+    tucker_cpu = None
+    if rank == 0 and world == 1 and not args.no_tucker and not args.no_cpu_baseline:
+        tucker_cpu = tucker_cpu_worker_start(args.tucker_nv, args.tucker_rank, args.tucker_eps)
     if world > 1:
         from vlasovtucker_b200 import multigpu
         runner = multigpu.WeakScaledBox(rank, world, local, hexes, cfg, brick=tuple(args.brick), dist=dist)
@@ -390,6 +633,21 @@ def run_gpu(args):
         except Exception as exc:   # the headline metric must not depend on this extra
             coupled = {"error": str(exc)[:300]}
 
+    # ---- Tucker format beside it (BASELINE.json's metric names both formats): C5 per-GPU share, same
+    # rank grid, after the full-format state has been released
+    tucker = None
+    if not args.no_tucker:
+        if runner is not None:
+            runner.ctx.close()
+        else:
+            ctx.close()
+        try:
+            tucker = run_tucker(args, (rank, world, local), dist, torch, tuple(args.tucker_hexes), args.tucker_nv,
+                                args.tucker_rank, args.tucker_eps, max(3, args.steps // 4), 2,
+                                cpu=not args.no_cpu_baseline, cpu_proc=tucker_cpu)
+        except Exception as exc:
+            tucker = {"error": str(exc)[:300]} if rank == 0 else None
+
     if rank == 0:
         peak, peak_src = measured_peak()
         kern_avg_ms = kern_ms / max(1, kern_n)
@@ -423,6 +681,8 @@ def run_gpu(args):
         }
         if coupled is not None:
             line["coupled_loop"] = coupled
+        if tucker is not None:
+            line["tucker"] = tucker
         if not args.no_cpu_baseline and world == 1:
             keep = {}
             cb, _ = cpu_legs(keep=keep)
@@ -431,6 +691,43 @@ def run_gpu(args):
                 line["parity"] = parity_vs_oracle(keep, local, args.variant, args.chunk_planes)
             except Exception as exc:
                 line["parity"] = {"error": str(exc)[:300]}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_gpu_tucker(args):
+    """`--format tucker`: the C5 line as the main JSON line."""
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    line = run_tucker(args, (rank, world, local), dist, torch, tuple(args.tucker_hexes), args.tucker_nv, args.tucker_rank,
+                      args.tucker_eps, args.steps, args.warmup, cpu=not args.no_cpu_baseline)
+    clocks = sampler.stop() if rank == 0 else None
+    sweep = []
+    if args.tucker_sweep:
+        for r in (4, 8, 12, 16):
+            for eps in (1e-4, 1e-6, 1e-8):
+                pt = run_tucker(args, (rank, world, local), dist, torch, (8, 8, 8), args.tucker_nv, r, eps, 2, 1, cpu=False)
+                if rank == 0:
+                    sweep.append({"max_rank": r, "compr_err": eps, "tets_per_gpu": pt["config"]["tets_per_gpu"],
+                                  "ms_per_step": pt["ms_per_step"], "value": pt["value"], "mean_rank_after": pt["config"]["mean_rank_after"],
+                                  "roofline_frac": pt["roofline"]["frac"], "executed_tflops": pt["roofline"]["executed_tflops"]})
+    if rank == 0:
+        line["vs_baseline"] = None
+        line["clocks"] = clocks
+        if sweep:
+            line["sweep"] = sweep
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -452,10 +749,23 @@ def main():
     ap.add_argument("--variant", type=int, default=64,
                     help="vt_step_config variant bits; 64 = the library's own choice (bulk-copy pipeline, upwind-select "
                          "arithmetic for 32^3), 2 = register-staged kernel")
+    ap.add_argument("--format", default="full", choices=["full", "tucker"],
+                    help="full: the headline line (with a `tucker` object beside it); tucker: the C5 Tucker line alone")
+    ap.add_argument("--tucker-hexes", type=int, nargs=3, default=[16, 16, 16], help="C5: hexes per GPU block")
+    ap.add_argument("--tucker-nv", type=int, default=48)
+    ap.add_argument("--tucker-rank", type=int, default=8, help="C5: rank of the initial condition = SetMaxRank")
+    ap.add_argument("--tucker-eps", type=float, default=1e-6, help="C5: comprErr")
+    ap.add_argument("--tucker-sweep", action="store_true",
+                    help="--format tucker: r in {4,8,12,16} x eps in {1e-4,1e-6,1e-8} on a reduced box, one object per point in `sweep`")
+    ap.add_argument("--no-tucker", action="store_true", help="skip the Tucker leg of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-coupled", action="store_true", help="skip the coupled-loop (Poisson + step) measurement")
     ap.add_argument("--cpu-worker", default=None, choices=["faithful", "fused"], help=argparse.SUPPRESS)
+    ap.add_argument("--tucker-cpu-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.tucker_cpu_worker:
+        print(json.dumps(tucker_cpu_baseline(args.tucker_nv, args.tucker_rank, args.tucker_eps)), flush=True)
+        return
     if args.cpu_worker:     # child of cpu_baseline_native: time one mode with the library VT_ORACLE_SO names
         explicit = any(a == "--steps" for a in sys.argv)
         cb = cpu_baseline(steps=args.steps if explicit else None, warmup=max(1, args.warmup), fused=args.cpu_worker == "fused",
@@ -466,6 +776,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.format == "tucker":
+        run_gpu_tucker(args)
     else:
         run_gpu(args)
 

@@ -84,6 +84,11 @@ int vt_species_get_pdf(vt_ctx* ctx, int species, int first, int count, double* p
 /* SetMaxwellPDF on the device (src/particle_data.cpp:23-90) */
 int vt_species_set_maxwell(vt_ctx* ctx, int species, const double* physDensity, double temperature,
                            const double mostProbableV[3]);
+/* pdf[t] = sum_k amp[t*nTerms+k] * a0_k (x) a1_k (x) a2_k, built on the device (a0: nTerms x n0, ...): the
+ * C5 inputs of the Tucker sweep — sums of shifted / anisotropic Maxwellians, multilinear rank nTerms —
+ * without a dense host array (the loop over tets of src/particle_data.cpp:33-66, generalised) */
+int vt_species_set_separable(vt_ctx* ctx, int species, int nTerms, const double* amp, const double* a0,
+                             const double* a1, const double* a2);
 /* ParticleData::Density (src/particle_data.cpp:93-102) and Velocity (:105-125);
  * out may be NULL (result stays on the device for the Poisson step) */
 int vt_species_density(vt_ctx* ctx, int species, double* density);
@@ -121,6 +126,9 @@ int vt_step_config(vt_ctx* ctx, int chunkPlanes, int brickTets, int variant);
 /* device time of the last vt_step_full kernel in milliseconds (CUDA events) and launches so far */
 int vt_step_last_ms(vt_ctx* ctx, float* ms);
 long vt_launch_count(vt_ctx* ctx);
+/* FP64 FMA peak of the device in TFLOP/s from a short register-resident probe (the denominator of
+ * the Tucker roofline; MEASURED_PEAKS.json carries no FP64 figure) */
+int vt_measure_dfma_peak(vt_ctx* ctx, double* tflops);
 /* measurement on the context's own stream (CUDA events): vt_profile_begin marks the start of a
  * timed region; vt_profile_end synchronises and returns the region's device time, the summed
  * device time of the step kernels launched inside it and how many there were */
@@ -162,11 +170,37 @@ int vt_wall_charge_reset(vt_ctx* ctx, int species);
  * — PoissonSolver::SetBC / Initialize (src/poisson.cpp:85-124) */
 int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceCentroid,
                      const uint8_t* bcType, const double* bcValue, const double* bcNormalGrad);
+/* ---- partitioned Poisson solve (one rank per GPU, or several contexts of one process): the rows are
+ * the rank's owned tets, ghost values of phi / z / grad(phi) arrive by peer stores, and the two dot
+ * products of every CG iteration are summed over the ranks inside the persistent solve kernel
+ * (rank-ordered, so every rank holds the same bits) — the role north_star gives an NCCL allreduce.
+ * No reference counterpart (the reference is one process); the matrix, right-hand side, correction and
+ * gradient are those of src/poisson.cpp, assembled per rank from its rows plus the ghost geometry.
+ *   vt_mesh_set_ghost_geometry  after vt_mesh_upload: globalId[nOwned+nGhost] = the reference's tet index of
+ *                               every local row (decides the Upper-triangle entry and the pinned row 0);
+ *                               per ghost tet its 4 neighbours as local indices (-1 = not on this rank),
+ *                               face areas, normals, centroid and face centroids
+ *   vt_poisson_set_global_dirichlet  before vt_poisson_setup: whether ANY rank holds a Dirichlet BC
+ *                               (poisson.cpp:87-88 decides the pinned row from it)
+ *   vt_poisson_comm_export      128-byte handle of this rank's exchange block (after vt_poisson_setup)
+ *   vt_poisson_comm_attach      all ranks' handles (world x 128 bytes, own entry ignored)
+ *   vt_poisson_comm_attach_local  the same for contexts of one process
+ *   vt_poisson_set_push         per owned tet (caller order) up to 4 (rank, ghost row on that rank) pairs */
+int vt_mesh_set_ghost_geometry(vt_ctx* ctx, int globalTets, const int32_t* globalId, const int32_t* ghostNbr,
+                               const double* ghostArea, const double* ghostNormal, const double* ghostTetCentroid,
+                               const double* ghostFaceCentroid);
+int vt_poisson_set_global_dirichlet(vt_ctx* ctx, int anyDirichlet);
+int vt_poisson_comm_export(vt_ctx* ctx, void* handle);
+int vt_poisson_comm_attach(vt_ctx* ctx, int myRank, int world, const void* handles);
+int vt_poisson_comm_attach_local(vt_ctx* ctx, int myRank, int world, vt_ctx* const* ranks);
+int vt_poisson_set_push(vt_ctx* ctx, const int32_t* pushRank, const int32_t* pushRow);
 /* Neumann/Dirichlet data may change between solves (src/solver.cpp:120-132) */
 int vt_poisson_update_bc_values(vt_ctx* ctx, const double* bcValue, const double* bcNormalGrad);
 /* PoissonSolver::Solve (src/poisson.cpp:179-213); rho NULL = use the device-resident charge
  * density assembled by vt_charge_density.  phi/E may be NULL. */
 int vt_poisson_solve(vt_ctx* ctx, const double* rho, double* phi, double* E);
+/* iterations and relative residual of the last solve (synchronises the context's stream: the solve
+ * itself is launched asynchronously) */
 int vt_poisson_stats(vt_ctx* ctx, int* lastIterations, double* lastRelResidual);
 /* rho = sum_s charge_s * Density_s + background (src/solver.cpp:98-105,
  * src/multicomponent_solver.cpp:61-74); background may be NULL */

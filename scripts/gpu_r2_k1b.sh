@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_full_gpu.py tests/test_virtual_ranks_gpu.py -q -m gpu -x 2>&1 | tail -8 | cut -c1-400 > gpurun_out/r2_pytest_full.log; cat gpurun_out/r2_pytest_full.log
+timeout 1500 python -m pytest tests/test_virtual_ranks_gpu.py tests/test_poisson_gpu.py -q -m gpu 2>&1 | tail -8 | cut -c1-400 > gpurun_out/r2_pytest_full.log; cat gpurun_out/r2_pytest_full.log
 rm -f gpurun_out/r2_sweep_k1b.jsonl
 timeout 900 python scripts/sweep_full.py --bricks "4,4,4;p4,1" --chunks "32,8" --variants "64,192,50,18" --steps 6 --out gpurun_out/r2_sweep_k1b.jsonl > gpurun_out/r2_sweep_k1b.log 2>&1
 python - <<'PY'

@@ -160,3 +160,93 @@ def test_virtual_ranks_tucker_bit_identical(vt):
     ctx.close()
     assert np.array_equal(ranks, rref)
     assert np.array_equal(full, ref), f"rel diff {rel_l2(full, ref):.3e}"
+
+
+# ---- partitioned Poisson solve (rows partitioned like the tets, ghost values by peer stores, the CG
+# dot products summed over the ranks inside the solve kernel) against the one-context solve and the oracle
+
+EPS0 = 8.85e-12
+PI = 3.14159265358979323846
+
+
+@pytest.mark.parametrize("mesh,pairs,spec,world", [
+    ("box_4955_tets.msh", [(5, 6)], {1: ("Dirichlet", 0, 0), 2: ("Dirichlet", 0, 0), 3: ("Neumann", 0, 0), 4: ("Neumann", 0, 0)}, 3),
+    ("fully_periodic_coarse.msh", [(1, 2), (3, 4), (5, 6)], {}, 2),          # pinned row 0 on one rank
+    ("rectangle_fine.msh", [(3, 4), (5, 6)], {1: ("Neumann", 0, 75.0), 2: ("Dirichlet", 0.5, 0)}, 4),
+])
+def test_virtual_ranks_poisson(vt, oracle_mod, mesh, pairs, spec, world):
+    from conftest import poisson_bc_arrays
+    from vlasovtucker_b200 import multigpu, partition as part
+    m = oracle_mod.Mesh.load(mesh_path(mesh), pairs)
+    mt = tables_from_oracle(m)
+    bc, val, ng = poisson_bc_arrays(m, spec)
+    c = m.tetCentroid
+    L = c.max(0)
+    rho = -EPS0 * np.cos(2 * PI * c[:, 1] / L[1]) * (1 + np.sin(2 * PI * c[:, 0] / L[0]))
+    p = oracle_mod.Poisson(m)
+    for e, (kind, v, g) in spec.items():
+        p.set_bc(e, kind, v, g)
+    p.initialize()
+    one = vt.Context(0)
+    one.mesh_upload(mt)
+    one.poisson_setup(bc, val, ng)
+    owner = part.rcb_owner(mt.tetCentroid, world)
+    vr = multigpu.VirtualRanks(mt, owner, world)
+    vr.poisson_setup(bc, val, ng)
+    for r in range(3):       # first call: two solves (uncorrected, corrected); later calls: warm start
+        phi_o, E_o = p.solve(rho * (1 + 0.1 * r))
+        phi_1, E_1 = one.poisson_solve(rho * (1 + 0.1 * r))
+        vr.poisson_solve(rho * (1 + 0.1 * r))
+        vr.sync()
+        got = [ctx.field_get() for ctx in vr.ctxs]
+        phi_p = vr.gather([g[1] for g in got])
+        E_p = vr.gather([g[2] for g in got])
+        its = [ctx.poisson_stats() for ctx in vr.ctxs]
+        assert len({i for i, _ in its}) == 1            # every rank took the same number of iterations
+        assert all(res <= 2.3e-16 for _, res in its)
+        # same algorithm, other summation order: cond(A) * eps apart
+        assert rel_l2(phi_p, phi_1) <= 1e-10, (r, rel_l2(phi_p, phi_1))
+        assert rel_l2(E_p, E_1) <= 1e-10, (r, rel_l2(E_p, E_1))
+        assert rel_l2(phi_p, phi_o) <= 1e-9
+        assert rel_l2(E_p, E_o) <= 1e-9
+    vr.close()
+    one.close()
+
+
+def test_virtual_ranks_coupled_loop(vt, oracle_mod):
+    """The whole loop body of Solver::Solve (solver.cpp:91-133) on three virtual ranks — charge density,
+    partitioned Poisson solve, partitioned step with fused halo — against one context and the oracle
+    (config C1s)."""
+    from conftest import poisson_bc_arrays
+    from vlasovtucker_b200 import multigpu, partition as part
+    m = oracle_mod.Mesh.load(mesh_path("rectangle.msh"), [(1, 2), (3, 4), (5, 6)])
+    mt = tables_from_oracle(m)
+    n, vmin, vmax, q, dt, steps, world = (11, 11, 11), [-3, -.1, -.1], [3, .1, .1], 2.975e-5, 1e-4, 20, 3
+    Lx = m.tetCentroid[:, 0].max() + m.tetCentroid[:, 0].min()
+    dens = 10 + 0.2 * np.sin(2 * PI * m.tetCentroid[:, 0] / Lx)
+    bg = -q * 10 * np.ones(m.nTets)
+    s = oracle_mod.Sim(m)
+    sp = s.add_species(n, vmin, vmax, 1.0, q)
+    s.set_maxwell(sp, dens, 0.0)
+    s.set_params(sp, dt, background=bg, fused=True)
+    s.begin()
+    qb, val, ng = poisson_bc_arrays(m, {})
+    owner = part.rcb_owner(mt.tetCentroid, world)
+    vr = multigpu.VirtualRanks(mt, owner, world)
+    ids = vr.species_create(n, vmin, vmax, 1.0, q)
+    for r, ctx in enumerate(vr.ctxs):
+        ctx.set_maxwell(ids[r], dens[vr.lps[r].owned], 0.0)
+    vr.fill_ghosts(ids)
+    vr.poisson_setup(qb, val, ng)
+    for it in range(steps):
+        s.step(it)
+        for r, ctx in enumerate(vr.ctxs):
+            ctx.charge_density([ids[r]], bg[vr.lps[r].owned])
+        vr.poisson_solve()
+        vr.step_full(ids, dt)
+    vr.sync()
+    f = vr.gather([ctx.get_pdf(ids[r]) for r, ctx in enumerate(vr.ctxs)])
+    phi = vr.gather([ctx.field_get()[1] for ctx in vr.ctxs])
+    vr.close()
+    assert rel_l2(f, s.get_pdf(sp)) <= 1e-10
+    assert rel_l2(phi, s.fields(sp)[1]) <= 1e-8

@@ -32,6 +32,8 @@ SIGNATURES = {
     "vt_species_set_pdf": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]),
     "vt_species_get_pdf": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_dp]),
     "vt_species_set_maxwell": (C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_double, c_dp]),
+    "vt_species_set_separable": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, c_dp, c_dp]),
+    "vt_measure_dfma_peak": (C.c_int, [C.c_void_p, c_dp]),
     "vt_species_density": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "vt_species_velocity": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "vt_field_set": (C.c_int, [C.c_void_p, c_dp]),
@@ -52,6 +54,12 @@ SIGNATURES = {
     "vt_wall_charge_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp]),
     "vt_wall_charge_reset": (C.c_int, [C.c_void_p, C.c_int]),
     "vt_poisson_setup": (C.c_int, [C.c_void_p, c_dp, c_dp, c_u8p, c_dp, c_dp]),
+    "vt_mesh_set_ghost_geometry": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_ip, c_dp, c_dp, c_dp, c_dp]),
+    "vt_poisson_set_global_dirichlet": (C.c_int, [C.c_void_p, C.c_int]),
+    "vt_poisson_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vt_poisson_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vt_poisson_comm_attach_local": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "vt_poisson_set_push": (C.c_int, [C.c_void_p, c_ip, c_ip]),
     "vt_poisson_update_bc_values": (C.c_int, [C.c_void_p, c_dp, c_dp]),
     "vt_poisson_solve": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
     "vt_poisson_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), c_dp]),

@@ -29,6 +29,15 @@ class MeshTables:
     brickTets: int = 0         # tets per L2 brick matching `order` (0 = library default)
     nGhost: int = 0
     periodic: list = field(default_factory=list)
+    # partition only (partition.partition fills them): the reference's tet index of every local row and
+    # the geometry of the ghost tets, which the partitioned Poisson assembly needs
+    globalTets: int = 0
+    globalId: np.ndarray = None          # (nT + nGhost,)
+    ghostNbr: np.ndarray = None          # (nGhost, 4) local index or -1
+    ghostArea: np.ndarray = None         # (nGhost, 4)
+    ghostNormal: np.ndarray = None       # (nGhost, 4, 3)
+    ghostTetCentroid: np.ndarray = None  # (nGhost, 3)
+    ghostFaceCentroid: np.ndarray = None  # (nGhost, 4, 3)
 
     @property
     def nTets(self):
@@ -79,6 +88,15 @@ class Context:
                                            capi.dp(vol), capi.dp(nrm), capi.ip(ent), capi.ip(order)))
         if mt.brickTets:
             self.step_config(brick_tets=mt.brickTets)
+        if mt.globalId is not None:
+            gid = capi.i32(mt.globalId)
+            gn = capi.i32(mt.ghostNbr if mt.nGhost else np.zeros((1, 4), np.int32))
+            ga = capi.f64(mt.ghostArea if mt.nGhost else np.zeros((1, 4)))
+            gnr = capi.f64(mt.ghostNormal if mt.nGhost else np.zeros((1, 4, 3)))
+            gc = capi.f64(mt.ghostTetCentroid if mt.nGhost else np.zeros((1, 3)))
+            gfc = capi.f64(mt.ghostFaceCentroid if mt.nGhost else np.zeros((1, 4, 3)))
+            capi.check(self.lib.vt_mesh_set_ghost_geometry(self.h, int(mt.globalTets), capi.ip(gid), capi.ip(gn), capi.dp(ga),
+                                                           capi.dp(gnr), capi.dp(gc), capi.dp(gfc)))
 
     # ---- species
     def species_create(self, n, vmin, vmax, mass, charge):
@@ -188,6 +206,18 @@ class Context:
     # ---- multi-GPU halo
     HALO_HANDLE_BYTES = 192
 
+    def set_separable(self, sp, amp, a0, a1, a2):
+        """pdf[t] = sum_k amp[t,k] a0[k] (x) a1[k] (x) a2[k], filled on the device."""
+        amp = capi.f64(amp).reshape(self.nOwned, -1)
+        k = amp.shape[1]
+        a0, a1, a2 = (capi.f64(a).reshape(k, -1) for a in (a0, a1, a2))
+        capi.check(self.lib.vt_species_set_separable(self.h, sp, k, capi.dp(amp), capi.dp(a0), capi.dp(a1), capi.dp(a2)))
+
+    def dfma_peak_tflops(self):
+        v = C.c_double()
+        capi.check(self.lib.vt_measure_dfma_peak(self.h, C.byref(v)))
+        return v.value
+
     def halo_export(self, sp):
         buf = np.zeros(self.HALO_HANDLE_BYTES, np.uint8)
         capi.check(self.lib.vt_halo_export(self.h, sp, buf.ctypes.data_as(C.c_void_p)))
@@ -226,6 +256,30 @@ class Context:
         tc = capi.f64(mt.tetCentroid)
         fc = capi.f64(mt.faceCentroid)
         capi.check(self.lib.vt_poisson_setup(self.h, capi.dp(tc), capi.dp(fc), capi.u8p(bc), capi.dp(val), capi.dp(ng)))
+
+    # partitioned solve (see include/vt_b200.h)
+    POISSON_HANDLE_BYTES = 128
+
+    def poisson_set_global_dirichlet(self, any_dirichlet):
+        capi.check(self.lib.vt_poisson_set_global_dirichlet(self.h, int(bool(any_dirichlet))))
+
+    def poisson_comm_export(self):
+        buf = np.zeros(self.POISSON_HANDLE_BYTES, np.uint8)
+        capi.check(self.lib.vt_poisson_comm_export(self.h, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    def poisson_comm_attach(self, my_rank, handles):
+        h = np.ascontiguousarray(handles, np.uint8).reshape(-1, self.POISSON_HANDLE_BYTES)
+        capi.check(self.lib.vt_poisson_comm_attach(self.h, int(my_rank), len(h), h.ctypes.data_as(C.c_void_p)))
+
+    def poisson_comm_attach_local(self, my_rank, ctxs):
+        arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        capi.check(self.lib.vt_poisson_comm_attach_local(self.h, int(my_rank), len(ctxs), arr))
+
+    def poisson_set_push(self, push_rank, push_row):
+        pr = capi.i32(push_rank).reshape(self.nOwned, 4)
+        prow = capi.i32(push_row).reshape(self.nOwned, 4)
+        capi.check(self.lib.vt_poisson_set_push(self.h, capi.ip(pr), capi.ip(prow)))
 
     def poisson_update_bc_values(self, bc_value, bc_normal_grad):
         val = capi.f64(bc_value)

@@ -17,8 +17,10 @@
 
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 
 namespace cg = cooperative_groups;
@@ -56,16 +58,62 @@ struct PoissonData {
     int* status = nullptr;         // [iterations, flag]
     double* statusD = nullptr;     // [residualNorm2, rhsNorm2]
     bool haveGradient = false;
+    bool statsPending = false;     // the last solve's status has not been read back yet
     int lastIterations = 0;
     double lastRelResidual = 0;
+    // ---- partitioned solve (multi-GPU): rows = owned tets, ghost values of x / z / grad arrive by peer
+    // stores, the two dot products of an iteration are summed over the ranks inside the kernel.
+    // One allocation holds everything a peer writes into: [x | z | grad | red | flagR | flagB].
+    int nTot = 0;                  // owned + ghost rows
+    void* xchg = nullptr;
+    size_t xchgBytes = 0;
+    double* red = nullptr;         // [2][kMaxRanks][2]: partial sums written by rank s, double buffered
+    uint32_t* flagR = nullptr;     // [2][kMaxRanks]: reduction epoch announced by rank s
+    uint32_t* flagB = nullptr;     // [kMaxRanks]: barrier epoch announced by rank s
+    int commRank = 0, commWorld = 1;
+    void* peerXchg[64] = {};       // base of every rank's exchange block (own entry = own block)
+    int peerNTot[64] = {};
+    void* commTable = nullptr;     // device copy of CommTable
+    int32_t* pushRank = nullptr;   // [4 * n] device order: rank that holds this row as a ghost, -1 unused
+    int32_t* pushRow = nullptr;    // ... and the ghost row there
+    uint32_t* epochDev = nullptr;  // reduction epoch counter, lives on the device across solves
+    uint32_t barEpoch = 0;
+    std::vector<void*> ipcOpened;
     double tol = std::numeric_limits<double>::epsilon();
     int gridBlocks = 0;
+    int globalRows = 0;            // rows of the whole system (= n on one GPU)
     std::vector<uint8_t> bcHost;       // caller order, 4 per tet
 };
 
 namespace {
 
 const double kEps0 = 8.85e-12;  // constants.h:10
+constexpr int kMaxRanks = 64;
+
+// what the kernels need to reach the other ranks (device memory, written once at attach time)
+struct CommTable {
+    double* x[kMaxRanks];
+    double* z[kMaxRanks];
+    double* grad[kMaxRanks];
+    double* red[kMaxRanks];
+    uint32_t* flagR[kMaxRanks];
+    uint32_t* flagB[kMaxRanks];
+};
+
+// layout of a rank's exchange block for nTot rows
+struct XchgLayout {
+    size_t x, z, grad, red, flagR, flagB, bytes;
+    explicit XchgLayout(size_t nTot)
+    {
+        x = 0;
+        z = x + nTot * sizeof(double);
+        grad = z + nTot * sizeof(double);
+        red = grad + 3 * nTot * sizeof(double);
+        flagR = red + 2 * kMaxRanks * 2 * sizeof(double);
+        flagB = flagR + 2 * kMaxRanks * sizeof(uint32_t);
+        bytes = flagB + kMaxRanks * sizeof(uint32_t);
+    }
+};
 
 struct PcgParams {
     int n;
@@ -86,6 +134,15 @@ struct PcgParams {
     double tol;
     int maxIters;
     int useGuess;
+    // partitioned solve
+    int nTot;                     // owned + ghost rows (x, z, p0, p1 have nTot entries)
+    int rank, world;
+    const CommTable* comm;
+    const int32_t* pushRank;
+    const int32_t* pushRow;
+    double* red;                  // own reduction slots
+    uint32_t* flagR;
+    uint32_t* epoch;
 };
 
 __device__ __forceinline__ double block_sum(double v, double* sh)
@@ -103,8 +160,15 @@ __device__ __forceinline__ double block_sum(double v, double* sh)
 // deterministic grid-wide sum of two values: per-CTA partials, one grid sync, then every CTA
 // re-sums all partials in the same fixed order.  Two partial buffers alternate so a buffer is
 // rewritten only after a later sync has retired all its readers.
-__device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double b, double* partial, int& buf,
-                                          double* sh, double& outA, double& outB)
+// COMM: the sum then goes over the ranks of a partitioned solve as well — CTA 0 stores this rank's
+// sums and the reduction epoch into every other rank's slots (peer stores), every CTA waits for the
+// other ranks' epochs in its own slots and adds the values in rank order, so that all CTAs of all
+// ranks hold bit-identical results.  Slots are double buffered by epoch parity: a rank can only be
+// one reduction ahead of the slowest one.  Peer stores issued before this call by any thread of the
+// grid (the z halo) are visible to a peer once it has seen the epoch (fence + grid sync + release).
+template <bool COMM>
+__device__ __forceinline__ void grid_sum2(cg::grid_group& grid, const PcgParams& P, uint32_t& epoch, double a, double b,
+                                          double* partial, int& buf, double* sh, double& outA, double& outB)
 {
     const double sa = block_sum(a, sh);
     const double sb = block_sum(b, sh);
@@ -114,6 +178,7 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double
         pb[2 * blockIdx.x] = sa;
         pb[2 * blockIdx.x + 1] = sb;
     }
+    if (COMM) __threadfence_system();
     grid.sync();
     double ta = 0.0, tb = 0.0;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
@@ -122,6 +187,41 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double
     }
     outA = block_sum(ta, sh);
     outB = block_sum(tb, sh);
+    if (COMM) {
+        epoch++;
+        const int par = epoch & 1u;
+        const int q = threadIdx.x;
+        if (q < P.world && q != P.rank) {
+            if (blockIdx.x == 0) {
+                double* dst = P.comm->red[q] + ((size_t)par * kMaxRanks + P.rank) * 2;
+                dst[0] = outA;
+                dst[1] = outB;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.comm->flagR[q] + par * kMaxRanks + P.rank), "r"(epoch)
+                             : "memory");
+            }
+            const uint32_t* in = P.flagR + par * kMaxRanks + q;
+            uint32_t v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(in) : "memory");
+            } while ((int32_t)(v - epoch) < 0);
+        }
+        __syncthreads();
+        double ga = 0.0, gb = 0.0;
+        for (int s = 0; s < P.world; s++) {
+            if (s == P.rank) {
+                ga += outA;
+                gb += outB;
+            } else {
+                const volatile double* src = P.red + ((size_t)par * kMaxRanks + s) * 2;
+                ga += src[0];
+                gb += src[1];
+            }
+        }
+        outA = ga;
+        outB = gb;
+        __syncthreads();
+    }
 }
 
 // Eigen 3.4 conjugate_gradient (ConjugateGradient.h:28-91) with the Jacobi preconditioner
@@ -129,6 +229,10 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, double a, double
 // iteration.  The search direction p = z + beta*p is recomputed on the fly for neighbour rows
 // inside the SpMV (from z and the previous p, both stable across the phase), which removes the
 // third sync a separate p-update would need.
+// COMM (partitioned solve): rows [n, nTot) are ghost rows.  x of the ghost rows was pushed by the
+// owners after the previous solve; z of the boundary rows is stored into the peers' ghost rows as it
+// is computed, right before the reduction that publishes it; p of a ghost row is advanced locally.
+template <bool COMM>
 __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
 {
     cg::grid_group grid = cg::this_grid();
@@ -136,9 +240,19 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
     int buf = 0;
+    uint32_t epoch = COMM ? *P.epoch : 0u;
+    const int nAll = COMM ? P.nTot : P.n;
+
+    auto push_z = [&](int i, double zi) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int rk = P.pushRank[4 * i + q];
+            if (rk >= 0) P.comm->z[rk][P.pushRow[4 * i + q]] = zi;
+        }
+    };
 
     if (!P.useGuess) {
-        for (int i = tid; i < P.n; i += nth) P.x[i] = 0.0;
+        for (int i = tid; i < nAll; i += nth) P.x[i] = 0.0;
         grid.sync();
     }
     // residual = rhs - A x ; rhsNorm2
@@ -157,46 +271,50 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
         l1 += ri * ri;
     }
     double rhsNorm2, residualNorm2;
-    grid_sum2(grid, l0, l1, P.partial, buf, sh, rhsNorm2, residualNorm2);
-    if (rhsNorm2 == 0.0) {
-        for (int i = tid; i < P.n; i += nth) P.x[i] = 0.0;
+    grid_sum2<COMM>(grid, P, epoch, l0, l1, P.partial, buf, sh, rhsNorm2, residualNorm2);
+    auto finish = [&](int it) {
         if (tid == 0) {
-            P.status[0] = 0;
-            P.statusD[0] = 0.0;
-            P.statusD[1] = 0.0;
+            P.status[0] = it;
+            P.statusD[0] = residualNorm2;
+            P.statusD[1] = rhsNorm2;
+            if (COMM) *P.epoch = epoch;
         }
+    };
+    if (rhsNorm2 == 0.0) {
+        for (int i = tid; i < nAll; i += nth) P.x[i] = 0.0;
+        residualNorm2 = 0.0;
+        finish(0);
         return;
     }
     const double threshold = fmax(P.tol * P.tol * rhsNorm2, 2.2250738585072014e-308);
     if (residualNorm2 < threshold) {
-        if (tid == 0) {
-            P.status[0] = 0;
-            P.statusD[0] = residualNorm2;
-            P.statusD[1] = rhsNorm2;
-        }
+        finish(0);
         return;
     }
     // z = M^-1 r ; absNew = r.z ; previous direction = 0 so that p = z + 0*p on the first pass
     double* pc = P.p0;
     double* pn = P.p1;
     l0 = 0.0;
-    for (int i = tid; i < P.n; i += nth) {
+    for (int i = tid; i < nAll; i += nth) {
+        pc[i] = 0.0;
+        if (i >= P.n) continue;
         const double zi = P.invDiag[i] * P.r[i];
         P.z[i] = zi;
-        pc[i] = 0.0;
+        if (COMM) push_z(i, zi);
         l0 += P.r[i] * zi;
     }
     double absNew, dummy;
-    grid_sum2(grid, l0, 0.0, P.partial, buf, sh, absNew, dummy);
+    grid_sum2<COMM>(grid, P, epoch, l0, 0.0, P.partial, buf, sh, absNew, dummy);
     double beta = 0.0;
 
     int it = 0;
     while (it < P.maxIters) {
         // p = z + beta p ; tmp = A p ; p.tmp
         l0 = 0.0;
-        for (int i = tid; i < P.n; i += nth) {
+        for (int i = tid; i < nAll; i += nth) {
             const double pi = P.z[i] + beta * pc[i];
             pn[i] = pi;
+            if (i >= P.n) continue;   // ghost row: only its search direction is advanced
             double t = P.diag[i] * pi;
 #pragma unroll
             for (int f = 0; f < 4; f++) {
@@ -208,7 +326,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
             l0 += pi * t;
         }
         double pAp;
-        grid_sum2(grid, l0, 0.0, P.partial, buf, sh, pAp, dummy);
+        grid_sum2<COMM>(grid, P, epoch, l0, 0.0, P.partial, buf, sh, pAp, dummy);
         const double alpha = absNew / pAp;
         // x += alpha p ; r -= alpha tmp ; z = M^-1 r ; |r|^2 ; r.z
         l0 = 0.0;
@@ -219,11 +337,12 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
             P.r[i] = ri;
             const double zi = P.invDiag[i] * ri;
             P.z[i] = zi;
+            if (COMM) push_z(i, zi);
             l0 += ri * ri;
             l1 += ri * zi;
         }
         double rz;
-        grid_sum2(grid, l0, l1, P.partial, buf, sh, residualNorm2, rz);
+        grid_sum2<COMM>(grid, P, epoch, l0, l1, P.partial, buf, sh, residualNorm2, rz);
         if (residualNorm2 < threshold) break;
         beta = rz / absNew;
         absNew = rz;
@@ -232,11 +351,36 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
         pn = t;
         it++;
     }
-    if (tid == 0) {
-        P.status[0] = it;
-        P.statusD[0] = residualNorm2;
-        P.statusD[1] = rhsNorm2;
+    finish(it);
+}
+
+// partitioned solve: copy k doubles per boundary row into the ghost rows of the ranks that hold it
+__global__ void k_push_vals(int n, int k, const double* __restrict__ src, const int32_t* __restrict__ pushRank,
+                            const int32_t* __restrict__ pushRow, double* const* __restrict__ peerBase)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int q = 0; q < 4; q++) {
+        const int rk = pushRank[4 * i + q];
+        if (rk < 0) continue;
+        double* dst = peerBase[rk] + (size_t)pushRow[4 * i + q] * k;
+        for (int c = 0; c < k; c++) dst[c] = src[(size_t)i * k + c];
     }
+}
+
+// partitioned solve: barrier over all ranks on the context stream (after the pushes above)
+__global__ void k_comm_barrier(const CommTable* comm, uint32_t* myFlags, int rank, int world, uint32_t epoch)
+{
+    const int q = threadIdx.x;
+    if (q >= world || q == rank) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(comm->flagB[q] + rank), "r"(epoch) : "memory");
+    const uint32_t* in = myFlags + q;
+    uint32_t v;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(in) : "memory");
+    } while ((int32_t)(v - epoch) < 0);
+    __threadfence_system();
 }
 
 // rhs_i = (-rho_i/eps0) V_i - sum_Dirichlet A/(d.n) value - sum_Neumann g A ; pinned row -> 0
@@ -403,6 +547,22 @@ void upload_bc_values(vt_ctx* ctx, PoissonData& P, const double* bcValue, const 
     VT_CUDA(cudaMemcpy(P.bcGrad, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice));
 }
 
+void read_stats(vt_ctx* ctx, PoissonData& P)
+{
+    if (!P.statsPending) return;
+    int st[2];
+    double sd[2];
+    VT_CUDA(cudaMemcpyAsync(st, P.status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    VT_CUDA(cudaMemcpyAsync(sd, P.statusD, sizeof(sd), cudaMemcpyDeviceToHost, ctx->stream));
+    VT_CUDA(cudaStreamSynchronize(ctx->stream));
+    P.lastIterations = st[0];
+    P.lastRelResidual = sd[1] > 0 ? std::sqrt(sd[0] / sd[1]) : 0.0;
+    P.statsPending = false;
+}
+
+// Launches the solve and returns: nothing here waits for the device (a partitioned solve driven by
+// one host thread — virtual ranks, several devices — must have every rank's kernel in flight before
+// any of them can finish); vt_poisson_stats reads the iteration count back on demand.
 void run_pcg(vt_ctx* ctx, PoissonData& P, bool useGuess)
 {
     PcgParams pp;
@@ -422,28 +582,51 @@ void run_pcg(vt_ctx* ctx, PoissonData& P, bool useGuess)
     pp.status = P.status;
     pp.statusD = P.statusD;
     pp.tol = P.tol;
-    pp.maxIters = 2 * P.n;   // IterativeSolverBase default
+    pp.maxIters = 2 * P.globalRows;   // IterativeSolverBase default: 2 * rows of the (global) system
     pp.useGuess = useGuess ? 1 : 0;
+    pp.nTot = P.nTot;
+    pp.rank = P.commRank;
+    pp.world = P.commWorld;
+    pp.comm = static_cast<const CommTable*>(P.commTable);
+    pp.pushRank = P.pushRank;
+    pp.pushRow = P.pushRow;
+    pp.red = P.red;
+    pp.flagR = P.flagR;
+    pp.epoch = P.epochDev;
     void* args[] = {&pp};
-    int blocks = std::min(P.gridBlocks, std::max(1, (P.n + 255) / 256));
-    VT_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(blocks), dim3(256), args, 0, ctx->stream));
+    int blocks = std::min(P.gridBlocks, std::max(1, (P.nTot + 255) / 256));
+    const bool comm = P.commWorld > 1;
+    if (comm && (!P.commTable || !P.pushRank))
+        throw std::runtime_error("partitioned Poisson: vt_poisson_comm_attach / vt_poisson_set_push have not been called");
+    VT_CUDA(cudaLaunchCooperativeKernel(comm ? (void*)k_pcg<true> : (void*)k_pcg<false>, dim3(blocks), dim3(256), args, 0,
+                                        ctx->stream));
     ctx->launches++;
-    int st[2];
-    double sd[2];
-    VT_CUDA(cudaMemcpyAsync(st, P.status, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
-    VT_CUDA(cudaMemcpyAsync(sd, P.statusD, sizeof(sd), cudaMemcpyDeviceToHost, ctx->stream));
-    VT_CUDA(cudaStreamSynchronize(ctx->stream));
-    P.lastIterations = st[0];
-    P.lastRelResidual = sd[1] > 0 ? std::sqrt(sd[0] / sd[1]) : 0.0;
+    P.statsPending = true;
+}
+
+// partitioned solve: boundary rows of `src` (k doubles per row) into the peers' ghost rows, then a
+// barrier over all ranks
+void push_and_barrier(vt_ctx* ctx, PoissonData& P, const double* src, int k, bool grad)
+{
+    if (P.commWorld <= 1) return;
+    const CommTable* ct = static_cast<const CommTable*>(P.commTable);
+    double* const* base = grad ? ct->grad : ct->x;   // device addresses of the pointer arrays inside the table
+    k_push_vals<<<(P.n + 127) / 128, 128, 0, ctx->stream>>>(P.n, k, src, P.pushRank, P.pushRow, base);
+    P.barEpoch++;
+    k_comm_barrier<<<1, kMaxRanks, 0, ctx->stream>>>(ct, P.flagB, P.commRank, P.commWorld, P.barEpoch);
+    ctx->launches += 2;
+    VT_CUDA(cudaGetLastError());
 }
 
 void gradient(vt_ctx* ctx, PoissonData& P)
 {
     const int n = P.n;
+    push_and_barrier(ctx, P, P.x, 1, false);      // phi of the ghost rows
     k_gradient<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, P.nbr, P.bc, P.dist, P.bcValue, P.bcGrad, P.x, P.grad,
                                                          ctx->E);
     ctx->launches++;
     VT_CUDA(cudaGetLastError());
+    push_and_barrier(ctx, P, P.grad, 3, true);    // gradient of the ghost rows, for the next correction
 }
 
 }  // namespace
@@ -454,8 +637,11 @@ void poisson_destroy(PoissonData* P)
     free_dev(P->nbr); free_dev(P->bc); free_dev(P->offU); free_dev(P->coefD); free_dev(P->area);
     free_dev(P->dist); free_dev(P->q); free_dev(P->wOwn); free_dev(P->wAdj); free_dev(P->bcValue);
     free_dev(P->bcGrad); free_dev(P->diag); free_dev(P->invDiag); free_dev(P->volume); free_dev(P->rhs);
-    free_dev(P->grad); free_dev(P->x); free_dev(P->r); free_dev(P->z); free_dev(P->tmp); free_dev(P->p[0]);
+    free_dev(P->r); free_dev(P->tmp); free_dev(P->p[0]);
     free_dev(P->p[1]); free_dev(P->partial); free_dev(P->status); free_dev(P->statusD);
+    for (void* q : P->ipcOpened) cudaIpcCloseMemHandle(q);
+    if (P->xchg) cudaFree(P->xchg);   // x, z, grad, reduction slots and flags live in this block
+    free_dev(P->commTable); free_dev(P->pushRank); free_dev(P->pushRow); free_dev(P->epochDev);
     delete P;
 }
 
@@ -470,34 +656,54 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
 {
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
-        if (ctx->nGhost > 0) throw std::runtime_error("vt_poisson_setup: multi-GPU Poisson is not wired to ghost rows yet");
+        if (ctx->nGhost > 0 && ctx->globalId.empty())
+            throw std::runtime_error("vt_poisson_setup on a partition needs vt_mesh_set_ghost_geometry first");
         if (ctx->poisson) poisson_destroy(ctx->poisson);
         ctx->poisson = new PoissonData();
         PoissonData& P = *ctx->poisson;
         const int n = P.n = ctx->nOwned;
+        const int nG = ctx->nGhost;
+        const int nTot = P.nTot = n + nG;
+        P.globalRows = ctx->globalRows > 0 ? ctx->globalRows : n;
         if (const char* t = std::getenv("VT_POISSON_TOL")) P.tol = std::atof(t);
-        auto C = [&](int t) { return V3{tetCentroid[3 * (size_t)t], tetCentroid[3 * (size_t)t + 1], tetCentroid[3 * (size_t)t + 2]}; };
+        // geometry of local row t (caller order): owned rows from the arguments and vt_mesh_upload,
+        // ghost rows (t >= n) from vt_mesh_set_ghost_geometry
+        auto C = [&](int t) {
+            const double* c = t < n ? tetCentroid + 3 * (size_t)t : ctx->ghostCentroid.data() + 3 * (size_t)(t - n);
+            return V3{c[0], c[1], c[2]};
+        };
         auto FC = [&](int t, int j) {
-            const size_t o = 12 * (size_t)t + 3 * j;
-            return V3{faceCentroid[o], faceCentroid[o + 1], faceCentroid[o + 2]};
+            const double* c = t < n ? faceCentroid + 12 * (size_t)t + 3 * j : ctx->ghostFaceCentroid.data() + 12 * (size_t)(t - n) + 3 * j;
+            return V3{c[0], c[1], c[2]};
         };
         auto NR = [&](int t, int j) {
-            const size_t o = 12 * (size_t)t + 3 * j;
-            return V3{ctx->normal[o], ctx->normal[o + 1], ctx->normal[o + 2]};
+            const double* c = t < n ? ctx->normal.data() + 12 * (size_t)t + 3 * j : ctx->ghostNormal.data() + 12 * (size_t)(t - n) + 3 * j;
+            return V3{c[0], c[1], c[2]};
         };
+        auto AREA = [&](int t, int j) { return t < n ? ctx->area[4 * (size_t)t + j] : ctx->ghostArea[4 * (size_t)(t - n) + j]; };
+        // the reference's tet index of a local row: decides which row of a pair holds the Upper entry
+        auto GID = [&](int t) { return ctx->globalId.empty() ? t : ctx->globalId[t]; };
         P.bcHost.assign(bcType, bcType + 4 * (size_t)n);
         P.solutionIsUnique = false;
         for (size_t i = 0; i < 4 * (size_t)n; i++)
             if (bcType[i] == VT_QBC_DIRICHLET) P.solutionIsUnique = true;   // poisson.cpp:87-88
-        P.pinnedRow = (!P.solutionIsUnique && n > 0) ? ctx->inv[0] : -1;   // poisson.cpp:128-134
+        // on a partition the Dirichlet faces may all belong to other ranks: vt_poisson_set_global_dirichlet
+        if (ctx->globalDirichlet >= 0) P.solutionIsUnique = ctx->globalDirichlet != 0;
+        // the pinned row is the reference's tet 0 (poisson.cpp:128-134): one rank owns it
+        P.pinnedRow = -1;
+        if (!P.solutionIsUnique)
+            for (int t = 0; t < n; t++)
+                if (GID(t) == 0) P.pinnedRow = ctx->inv[t];
 
-        // caller-order neighbour table
-        std::vector<int32_t> adj(4 * (size_t)n);
+        // caller-order neighbour table over owned and ghost rows
+        std::vector<int32_t> adj(4 * (size_t)nTot, -1);
         for (int p = 0; p < n; p++)
             for (int j = 0; j < 4; j++) {
                 const int a = ctx->nbrHost[4 * (size_t)p + j];
-                adj[4 * (size_t)ctx->order[p] + j] = a < 0 ? -1 : ctx->order[a];
+                adj[4 * (size_t)ctx->order[p] + j] = a < 0 ? -1 : (a < n ? ctx->order[a] : a);
             }
+        for (int g = 0; g < nG; g++)
+            for (int j = 0; j < 4; j++) adj[4 * (size_t)(n + g) + j] = ctx->ghostNbr[4 * (size_t)g + j];
         // d for interior/periodic faces (poisson.cpp:145-162): periodic adds the plane offset
         auto faceDistance = [&](int t, int j, int bc) {
             const int a = adj[4 * (size_t)t + j];
@@ -510,6 +716,8 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
             }
             return d;
         };
+        // A/(d.n) of face j of local row t (owned or ghost); the BC kind of a pair face is the same on both sides
+        auto coefOf = [&](int t, int j, int bc) { return AREA(t, j) / dot(faceDistance(t, j, bc), NR(t, j)); };
         std::vector<double> coef(4 * (size_t)n, 0.0);    // caller order: this row's A/(d.n)
         for (int t = 0; t < n; t++)
             for (int j = 0; j < 4; j++) {
@@ -517,7 +725,7 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
                 const int bc = bcType[fi];
                 if (bc == VT_QBC_NONBOUNDARY || bc == VT_QBC_PERIODIC) {
                     if (adj[fi] < 0) throw std::runtime_error("Poisson: boundary face without a field BC (null adjTets, poisson.cpp:142-147)");
-                    coef[fi] = ctx->area[fi] / dot(faceDistance(t, j, bc), NR(t, j));
+                    coef[fi] = coefOf(t, j, bc);
                 } else if (bc == VT_QBC_DIRICHLET) {
                     coef[fi] = ctx->area[fi] / dot(sub(FC(t, j), C(t)), NR(t, j));
                 }
@@ -541,14 +749,14 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
                 bool hasE = false;
                 if (bc == VT_QBC_NONBOUNDARY || bc == VT_QBC_PERIODIC) {
                     const int a = adj[fi];
-                    nbrD[fo] = ctx->inv[a];
+                    nbrD[fo] = a < n ? ctx->inv[a] : a;
                     dg += -coef[fi];
                     // Upper view: coefficient assembled in the row with the smaller reference index;
                     // the pinned row 0 holds only its diagonal (poisson.cpp:128-134)
                     double w;
-                    if (a > t) w = (pinned && t == 0) ? 0.0 : coef[fi];
-                    else if (a < t) {
-                        if (pinned && a == 0) w = 0.0;
+                    if (a != t && GID(a) > GID(t)) w = (pinned && GID(t) == 0) ? 0.0 : coef[fi];
+                    else if (a != t) {
+                        if (pinned && GID(a) == 0) w = 0.0;
                         else {
                             // sum of the neighbour row's entries towards t is split per face: use the
                             // back face matching this one (first k with adj[a][k]==t, duplicates in order)
@@ -562,7 +770,7 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
                                     cnt++;
                                 }
                             if (k < 0) throw std::runtime_error("adjacency is not symmetric");
-                            w = coef[4 * (size_t)a + k];
+                            w = a < n ? coef[4 * (size_t)a + k] : coefOf(a, k, bc);
                         }
                     } else {
                         w = 0.0;   // self-neighbour: folded into the diagonal below
@@ -598,7 +806,7 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
                     q[12 * (size_t)p + 3 * j + 2] = qq.z;
                 }
             }
-            if (pinned && t == 0) {
+            if (pinned && GID(t) == 0) {
                 dg = 1.0;
                 for (int j = 0; j < 4; j++) offU[4 * (size_t)p + j] = 0.0;
             }
@@ -621,19 +829,183 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
         VT_CUDA(cudaMalloc(&P.bcValue, 4 * nA * sizeof(double)));
         VT_CUDA(cudaMalloc(&P.bcGrad, 4 * nA * sizeof(double)));
         upload_bc_values(ctx, P, bcValue, bcNormalGrad);
-        for (double** v : {&P.rhs, &P.x, &P.r, &P.z, &P.tmp, &P.p[0], &P.p[1]}) {
+        const size_t nT = std::max(1, nTot);
+        for (double** v : {&P.rhs, &P.r, &P.tmp}) {
             VT_CUDA(cudaMalloc(v, nA * sizeof(double)));
             VT_CUDA(cudaMemset(*v, 0, nA * sizeof(double)));
         }
-        VT_CUDA(cudaMalloc(&P.grad, 3 * nA * sizeof(double)));
-        VT_CUDA(cudaMemset(P.grad, 0, 3 * nA * sizeof(double)));
+        for (double** v : {&P.p[0], &P.p[1]}) {
+            VT_CUDA(cudaMalloc(v, nT * sizeof(double)));
+            VT_CUDA(cudaMemset(*v, 0, nT * sizeof(double)));
+        }
+        // everything a peer rank writes into lives in one block (one CUDA-IPC handle)
+        const XchgLayout lay(nT);
+        P.xchgBytes = lay.bytes;
+        VT_CUDA(cudaMalloc(&P.xchg, lay.bytes));
+        VT_CUDA(cudaMemset(P.xchg, 0, lay.bytes));
+        char* xb = static_cast<char*>(P.xchg);
+        P.x = reinterpret_cast<double*>(xb + lay.x);
+        P.z = reinterpret_cast<double*>(xb + lay.z);
+        P.grad = reinterpret_cast<double*>(xb + lay.grad);
+        P.red = reinterpret_cast<double*>(xb + lay.red);
+        P.flagR = reinterpret_cast<uint32_t*>(xb + lay.flagR);
+        P.flagB = reinterpret_cast<uint32_t*>(xb + lay.flagB);
+        VT_CUDA(cudaMalloc(&P.epochDev, sizeof(uint32_t)));
+        VT_CUDA(cudaMemset(P.epochDev, 0, sizeof(uint32_t)));
         int perSm = 0;
-        VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg, 256, 0));
+        VT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_pcg<true>, 256, 0));
         P.gridBlocks = std::max(1, std::min(perSm, 2) * ctx->prop.multiProcessorCount);
         VT_CUDA(cudaMalloc(&P.partial, 4 * (size_t)P.gridBlocks * sizeof(double)));
         VT_CUDA(cudaMalloc(&P.status, 2 * sizeof(int)));
         VT_CUDA(cudaMalloc(&P.statusD, 2 * sizeof(double)));
         P.haveGradient = false;
+        return 0;
+    } catch (std::exception& e) {
+        vt_set_error(e.what());
+        return 1;
+    }
+}
+
+// ---- partitioned solve: wiring of the ranks ---------------------------------------------------------
+struct PoissonIpc {
+    cudaIpcMemHandle_t block;
+    long long nTot;
+    unsigned char pad[56];
+};
+static_assert(sizeof(PoissonIpc) == 128, "Poisson comm handle is 128 bytes");
+
+static void fill_comm_table(vt_ctx* ctx, PoissonData& P)
+{
+    CommTable tb;
+    std::memset(&tb, 0, sizeof(tb));
+    for (int r = 0; r < P.commWorld; r++) {
+        char* base = static_cast<char*>(P.peerXchg[r]);
+        if (!base) continue;
+        const XchgLayout lay((size_t)std::max(1, P.peerNTot[r]));
+        tb.x[r] = reinterpret_cast<double*>(base + lay.x);
+        tb.z[r] = reinterpret_cast<double*>(base + lay.z);
+        tb.grad[r] = reinterpret_cast<double*>(base + lay.grad);
+        tb.red[r] = reinterpret_cast<double*>(base + lay.red);
+        tb.flagR[r] = reinterpret_cast<uint32_t*>(base + lay.flagR);
+        tb.flagB[r] = reinterpret_cast<uint32_t*>(base + lay.flagB);
+    }
+    if (!P.commTable) VT_CUDA(cudaMalloc(&P.commTable, sizeof(CommTable)));
+    VT_CUDA(cudaMemcpy(P.commTable, &tb, sizeof(tb), cudaMemcpyHostToDevice));
+}
+
+int vt_poisson_set_global_dirichlet(vt_ctx* ctx, int anyDirichlet)
+{
+    ctx->globalDirichlet = anyDirichlet ? 1 : 0;
+    return 0;
+}
+
+int vt_poisson_comm_export(vt_ctx* ctx, void* handle)
+{
+    try {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
+        PoissonIpc pk;
+        std::memset(&pk, 0, sizeof(pk));
+        VT_CUDA(cudaIpcGetMemHandle(&pk.block, ctx->poisson->xchg));
+        pk.nTot = ctx->poisson->nTot;
+        std::memcpy(handle, &pk, sizeof(pk));
+        return 0;
+    } catch (std::exception& e) {
+        vt_set_error(e.what());
+        return 1;
+    }
+}
+
+int vt_poisson_comm_attach(vt_ctx* ctx, int myRank, int world, const void* handles)
+{
+    try {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
+        if (world < 1 || world > kMaxRanks || myRank < 0 || myRank >= world) throw std::invalid_argument("bad rank / world size");
+        PoissonData& P = *ctx->poisson;
+        P.commRank = myRank;
+        P.commWorld = world;
+        const PoissonIpc* pk = static_cast<const PoissonIpc*>(handles);
+        for (int r = 0; r < world; r++) {
+            if (r == myRank) {
+                P.peerXchg[r] = P.xchg;
+                P.peerNTot[r] = P.nTot;
+                continue;
+            }
+            void* base = nullptr;
+            VT_CUDA(cudaIpcOpenMemHandle(&base, pk[r].block, cudaIpcMemLazyEnablePeerAccess));
+            P.ipcOpened.push_back(base);
+            P.peerXchg[r] = base;
+            P.peerNTot[r] = (int)pk[r].nTot;
+        }
+        fill_comm_table(ctx, P);
+        return 0;
+    } catch (std::exception& e) {
+        vt_set_error(e.what());
+        return 1;
+    }
+}
+
+int vt_poisson_comm_attach_local(vt_ctx* ctx, int myRank, int world, vt_ctx* const* ranks)
+{
+    try {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
+        if (world < 1 || world > kMaxRanks || myRank < 0 || myRank >= world) throw std::invalid_argument("bad rank / world size");
+        PoissonData& P = *ctx->poisson;
+        P.commRank = myRank;
+        P.commWorld = world;
+        int sameDevice = 0;
+        for (int r = 0; r < world; r++) {
+            vt_ctx* pc = ranks[r];
+            if (!pc || !pc->poisson) throw std::runtime_error("vt_poisson_comm_attach_local: a rank has no Poisson set-up yet");
+            if (pc->device == ctx->device) sameDevice++;
+            else {
+                int can = 0;
+                VT_CUDA(cudaDeviceCanAccessPeer(&can, ctx->device, pc->device));
+                if (!can) throw std::runtime_error("vt_poisson_comm_attach_local: no peer access between the devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(pc->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) VT_CUDA(e);
+                (void)cudaGetLastError();
+            }
+            P.peerXchg[r] = pc->poisson->xchg;
+            P.peerNTot[r] = pc->poisson->nTot;
+        }
+        // ranks that share this device ("virtual ranks") run their persistent solve kernels side by side:
+        // each takes its share of the co-resident CTAs, or they would wait for each other forever
+        P.gridBlocks = std::max(1, P.gridBlocks / std::max(1, sameDevice));
+        fill_comm_table(ctx, P);
+        return 0;
+    } catch (std::exception& e) {
+        vt_set_error(e.what());
+        return 1;
+    }
+}
+
+int vt_poisson_set_push(vt_ctx* ctx, const int32_t* pushRank, const int32_t* pushRow)
+{
+    try {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
+        PoissonData& P = *ctx->poisson;
+        const int n = P.n;
+        std::vector<int32_t> pr(4 * (size_t)std::max(1, n), -1), prow(4 * (size_t)std::max(1, n), -1);
+        for (int p = 0; p < n; p++) {
+            const int t = ctx->order[p];
+            int used = 0;
+            for (int j = 0; j < 4; j++) {
+                const int rk = pushRank[4 * (size_t)t + j];
+                if (rk < 0) continue;
+                if (rk >= kMaxRanks) throw std::invalid_argument("push rank out of range");
+                pr[4 * (size_t)p + used] = rk;
+                prow[4 * (size_t)p + used] = pushRow[4 * (size_t)t + j];
+                used++;
+            }
+        }
+        free_dev(P.pushRank);
+        free_dev(P.pushRow);
+        P.pushRank = to_device(pr);
+        P.pushRow = to_device(prow);
         return 0;
     } catch (std::exception& e) {
         vt_set_error(e.what());
@@ -706,6 +1078,13 @@ int vt_poisson_solve(vt_ctx* ctx, const double* rho, double* phi, double* E)
 int vt_poisson_stats(vt_ctx* ctx, int* lastIterations, double* lastRelResidual)
 {
     if (!ctx->poisson) return 1;
+    try {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        read_stats(ctx, *ctx->poisson);
+    } catch (std::exception& e) {
+        vt_set_error(e.what());
+        return 1;
+    }
     if (lastIterations) *lastIterations = ctx->poisson->lastIterations;
     if (lastRelResidual) *lastRelResidual = ctx->poisson->lastRelResidual;
     return 0;

@@ -1243,9 +1243,21 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
             VT_CUDA(cudaMemsetAsync(profDev, 0, 8 * sizeof(long long), ctx->stream));
             P.prof = profDev;
         }
-        VT_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
+        if (ctx->profiling) {   // vt_profile_begin/end: one event pair per step-kernel launch
+            if (ctx->kernelEventsUsed + 2 > ctx->kernelEvents.size()) {
+                cudaEvent_t a, b;
+                VT_CUDA(cudaEventCreate(&a));
+                VT_CUDA(cudaEventCreate(&b));
+                ctx->kernelEvents.push_back(a);
+                ctx->kernelEvents.push_back(b);
+            }
+            e0 = ctx->kernelEvents[ctx->kernelEventsUsed++];
+            e1 = ctx->kernelEvents[ctx->kernelEventsUsed++];
+        }
+        VT_CUDA(cudaEventRecord(e0, ctx->stream));
         launch(ctx, ts, P);
-        VT_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        VT_CUDA(cudaEventRecord(e1, ctx->stream));
         if (profile) {
             long long h[8];
             VT_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -49,6 +49,34 @@ __global__ void k_maxwell_fill(double* __restrict__ f, const double* __restrict_
     double* d = f + (size_t)row * N;
     for (int e = threadIdx.x; e < N; e += blockDim.x) d[e] = table[e] * s;
 }
+// f[row][e] = sum_k amp[row][k] * a0[k][i0] * a1[k][i1] * a2[k][i2]: a sum of nTerms separable terms
+// (shifted / anisotropic Maxwellians of the C5 inputs: multilinear rank nTerms exactly)
+__global__ void k_separable_fill(double* __restrict__ f, const double* __restrict__ amp, const double* __restrict__ a0,
+                                 const double* __restrict__ a1, const double* __restrict__ a2, int nTerms, int n0, int n1,
+                                 int n2)
+{
+    const int row = blockIdx.x;
+    const int N = n0 * n1 * n2;
+    double* d = f + (size_t)row * N;
+    for (int e = threadIdx.x; e < N; e += blockDim.x) {
+        const int i0 = e % n0, i1 = (e / n0) % n1, i2 = e / (n0 * n1);
+        double s = 0.0;
+        for (int k = 0; k < nTerms; k++)
+            s += amp[(size_t)row * nTerms + k] * ((a0[k * n0 + i0] * a1[k * n1 + i1]) * a2[k * n2 + i2]);
+        d[e] = s;
+    }
+}
+// FP64 FMA peak probe: 8 independent chains per thread
+__global__ void k_dfma_probe(double* out, int iters)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
 // u_k = sum_v v_k f * cellVolume / density   (particle_data.cpp:105-125)
 __global__ void k_velocity(const double* __restrict__ f, const double* __restrict__ density,
                            double* __restrict__ vel, int n0, int n1, int n2, double m0, double m1,
@@ -347,6 +375,25 @@ int vt_mesh_upload(vt_ctx* ctx, int nOwned, int nGhost, const int32_t* nbr, cons
     });
 }
 
+int vt_mesh_set_ghost_geometry(vt_ctx* ctx, int globalTets, const int32_t* globalId, const int32_t* ghostNbr,
+                               const double* ghostArea, const double* ghostNormal, const double* ghostTetCentroid,
+                               const double* ghostFaceCentroid)
+{
+    return guard([&] {
+        const size_t nO = ctx->nOwned, nG = ctx->nGhost;
+        if (globalTets < (int)nO) throw std::invalid_argument("vt_mesh_set_ghost_geometry: globalTets < nOwned");
+        ctx->globalRows = globalTets;
+        ctx->globalId.assign(globalId, globalId + nO + nG);
+        ctx->ghostNbr.assign(ghostNbr, ghostNbr + 4 * nG);
+        for (size_t i = 0; i < 4 * nG; i++)
+            if (ctx->ghostNbr[i] >= (int)(nO + nG)) throw std::invalid_argument("ghost neighbour index out of range");
+        ctx->ghostArea.assign(ghostArea, ghostArea + 4 * nG);
+        ctx->ghostNormal.assign(ghostNormal, ghostNormal + 12 * nG);
+        ctx->ghostCentroid.assign(ghostTetCentroid, ghostTetCentroid + 3 * nG);
+        ctx->ghostFaceCentroid.assign(ghostFaceCentroid, ghostFaceCentroid + 12 * nG);
+    });
+}
+
 int vt_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], const double vmax[3], double mass,
                       double charge, int* species)
 {
@@ -530,6 +577,64 @@ int vt_species_set_maxwell(vt_ctx* ctx, int species, const double* physDensity, 
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
         sp.densityValid = false;
         if (sp.tucker) vt::tucker_from_dense(ctx, sp);
+    });
+}
+
+int vt_species_set_separable(vt_ctx* ctx, int species, int nTerms, const double* amp, const double* a0,
+                             const double* a1, const double* a2)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        vt::Species& sp = species_of(ctx, species);
+        if (nTerms < 1 || nTerms > 64) throw std::invalid_argument("vt_species_set_separable: 1..64 terms");
+        const int n = ctx->nOwned;
+        if (n == 0) return;
+        const size_t nAmp = (size_t)n * nTerms, nAx = (size_t)nTerms * (sp.n[0] + sp.n[1] + sp.n[2]);
+        double* dev = vt::ctx_stage(ctx, (nAmp + nAx) * sizeof(double));
+        std::vector<double> host(nAmp + nAx);
+        for (int p = 0; p < n; p++)
+            for (int k = 0; k < nTerms; k++) host[(size_t)p * nTerms + k] = amp[(size_t)ctx->order[p] * nTerms + k];
+        double* h = host.data() + nAmp;
+        std::memcpy(h, a0, (size_t)nTerms * sp.n[0] * sizeof(double));
+        std::memcpy(h + (size_t)nTerms * sp.n[0], a1, (size_t)nTerms * sp.n[1] * sizeof(double));
+        std::memcpy(h + (size_t)nTerms * (sp.n[0] + sp.n[1]), a2, (size_t)nTerms * sp.n[2] * sizeof(double));
+        VT_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        const double* d0 = dev + nAmp;
+        k_separable_fill<<<n, 256, 0, ctx->stream>>>(sp.f[sp.cur], dev, d0, d0 + (size_t)nTerms * sp.n[0],
+                                                     d0 + (size_t)nTerms * (sp.n[0] + sp.n[1]), nTerms, sp.n[0], sp.n[1],
+                                                     sp.n[2]);
+        ctx->launches++;
+        VT_CUDA(cudaGetLastError());
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
+        sp.densityValid = false;
+        if (sp.tucker) vt::tucker_from_dense(ctx, sp);
+    });
+}
+
+int vt_measure_dfma_peak(vt_ctx* ctx, double* tflops)
+{
+    return guard([&] {
+        VT_CUDA(cudaSetDevice(ctx->device));
+        const int blocks = 8 * ctx->prop.multiProcessorCount, threads = 256, iters = 20000;
+        double* out = vt::ctx_stage(ctx, (size_t)blocks * threads * sizeof(double));
+        cudaEvent_t e0, e1;
+        VT_CUDA(cudaEventCreate(&e0));
+        VT_CUDA(cudaEventCreate(&e1));
+        k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(out, iters);   // warm-up
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            VT_CUDA(cudaEventRecord(e0, ctx->stream));
+            k_dfma_probe<<<blocks, threads, 0, ctx->stream>>>(out, iters);
+            VT_CUDA(cudaEventRecord(e1, ctx->stream));
+            VT_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            VT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            best = std::min(best, ms);
+        }
+        ctx->launches += 4;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *tflops = 2.0 * 8 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
     });
 }
 

@@ -116,6 +116,13 @@ struct vt_ctx {
     std::vector<int32_t> entity;                // caller order
     int32_t* orderDev = nullptr;
     int32_t* invDev = nullptr;
+    // partitioned mesh (vt_mesh_set_ghost_geometry): what the Poisson assembly needs to know about
+    // the ghost tets, and the reference's (global) tet index of every local row
+    std::vector<int32_t> globalId;              // [nOwned + nGhost], caller order; empty = identity
+    std::vector<int32_t> ghostNbr;              // [4 * nGhost] local caller index across each ghost face, -1 = not local
+    std::vector<double> ghostArea, ghostNormal, ghostCentroid, ghostFaceCentroid;
+    int globalRows = 0;                         // tets of the whole mesh (0 = nOwned)
+    int globalDirichlet = -1;                   // partition: does ANY rank hold a Dirichlet field BC (-1 = decide locally)
 
     std::vector<vt::Species*> species;
 

@@ -84,6 +84,25 @@ class VirtualRanks:
                     ctx.tucker_halo_attach_local(ids[r], [self.ctxs[q] for q in lp.peers], [ids[q] for q in lp.peers])
         return ids
 
+    def poisson_setup(self, bc_type, bc_value=None, bc_normal_grad=None):
+        """Partitioned PoissonSolver: every rank assembles its rows (global (nTets, 4) BC arrays in),
+        then the ranks are wired to each other (ghost values by peer stores, in-kernel reductions)."""
+        any_dirichlet = bool(np.any(np.asarray(bc_type) == 2))
+        for ctx, lp in zip(self.ctxs, self.lps):
+            ctx.poisson_set_global_dirichlet(any_dirichlet)
+            ctx.poisson_setup(np.asarray(bc_type)[lp.owned],
+                              None if bc_value is None else np.asarray(bc_value)[lp.owned],
+                              None if bc_normal_grad is None else np.asarray(bc_normal_grad)[lp.owned])
+        for r, (ctx, lp) in enumerate(zip(self.ctxs, self.lps)):
+            ctx.poisson_comm_attach_local(r, self.ctxs)
+            ctx.poisson_set_push(lp.push_rank, lp.push_row)
+
+    def poisson_solve(self, rho=None):
+        """Launch every rank's solve (nothing waits on the host in between); rho = global array or None
+        (device-resident charge density)."""
+        for ctx, lp in zip(self.ctxs, self.lps):
+            ctx.poisson_solve(None if rho is None else np.asarray(rho)[lp.owned], download=False)
+
     def scatter(self, a):
         """Global per-tet array -> list of per-rank owned slices."""
         return [np.ascontiguousarray(a[lp.owned]) for lp in self.lps]
@@ -130,7 +149,10 @@ class WeakScaledBox:
     """Config C4 weak scaling: every rank owns one block of `hexes` Kuhn hexes of a periodic box
     that is `rank_grid(world)` blocks large."""
 
-    def __init__(self, rank, world, local_device, hexes, cfg, brick, dist):
+    def __init__(self, rank, world, local_device, hexes, cfg, brick, dist, tucker=None, init=None):
+        """tucker = (comprErr, maxRank): the species is kept in Tucker format; init(ctx, sp, x) sets the
+        initial distribution functions from the normalised x coordinate of the owned tets (default:
+        the C4 Maxwellian with a 1 % density wave)."""
         self.rank, self.world, self.dist = rank, world, dist
         grid = part.rank_grid(world)
         ghex = tuple(h * g for h, g in zip(hexes, grid))
@@ -144,10 +166,15 @@ class WeakScaledBox:
         self.mt = lp.tables
         self.ctx = ctx = Context(local_device)
         ctx.mesh_upload(lp.tables)
-        self.ps = PartitionedSpecies(ctx, lp, dist, cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"])
+        self.ps = PartitionedSpecies(ctx, lp, dist, cfg["n"], cfg["vmin"], cfg["vmax"], cfg["mass"], cfg["charge"],
+                                     tucker=tucker)
         self.sp = self.ps.sp
+        self.tucker = tucker is not None
         x = lp.tables.tetCentroid[:, 0] / glen[0]
-        ctx.set_maxwell(self.sp, cfg["dens"] * (1 + 0.01 * np.sin(2 * PI * x)), cfg["T"])
+        if init is not None:
+            init(ctx, self.sp, x)
+        else:
+            ctx.set_maxwell(self.sp, cfg["dens"] * (1 + 0.01 * np.sin(2 * PI * x)), cfg["T"])
         self.E = np.zeros((lp.tables.nTets, 3))
         self.E[:, 0] = 1e3 * np.cos(2 * PI * x)
         ctx.field_set(self.E)
@@ -155,22 +182,54 @@ class WeakScaledBox:
         dist.barrier()
 
     def step(self, dt):
-        self.ctx.step_full(self.sp, dt)
+        if self.tucker:
+            self.ctx.step_tucker(self.sp, dt)
+        else:
+            self.ctx.step_full(self.sp, dt)
+        self.ctx.halo_barrier()
+
+    def step_host(self, dt, dens):
+        """One step through host buffers: E in, Density() out."""
+        if self.tucker:
+            self.ctx.field_set(self.E)
+            self.ctx.step_tucker(self.sp, dt)
+            dens[:] = self.ctx.tucker_density(self.sp)
+        else:
+            self.ctx.step_full_host(self.sp, dt, self.E, dens)
         self.ctx.halo_barrier()
 
     def e2e(self, dt, steps, barrier):
         import time
         dens = np.empty(self.mt.nTets)
-        self.ctx.step_full_host(self.sp, dt, self.E, dens)
-        self.ctx.halo_barrier()
+        self.step_host(dt, dens)
         barrier()
         t0 = time.perf_counter()
         self.ctx.profile_begin()
         for _ in range(steps):
-            self.ctx.step_full_host(self.sp, dt, self.E, dens)
-            self.ctx.halo_barrier()
+            self.step_host(dt, dens)
         region_ms, _, _ = self.ctx.profile_end()
         return max(region_ms, (time.perf_counter() - t0) * 1e3)
+
+
+class PartitionedPoisson:
+    """PoissonSolver of a partitioned run, one process per GPU: rows = owned tets, phi / z / grad(phi) of
+    the ghost rows by peer stores (CUDA-IPC), the dot products of every CG iteration summed over the
+    ranks inside the solve kernel.  torch.distributed only carries the 128-byte handles at set-up."""
+
+    def __init__(self, ctx, lp, dist, bc_type, bc_value=None, bc_normal_grad=None, any_dirichlet=None):
+        world = dist.get_world_size()
+        if any_dirichlet is None:
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(np.any(np.asarray(bc_type) == 2)))
+            any_dirichlet = any(flags)
+        ctx.poisson_set_global_dirichlet(any_dirichlet)
+        ctx.poisson_setup(bc_type, bc_value, bc_normal_grad)
+        mine = ctx.poisson_comm_export()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine.tobytes())
+        ctx.poisson_comm_attach(lp.rank, np.stack([np.frombuffer(g, np.uint8) for g in gathered]))
+        ctx.poisson_set_push(lp.push_rank, lp.push_row)
+        dist.barrier()
 
 
 class ReplicatedField:

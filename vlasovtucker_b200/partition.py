@@ -29,6 +29,7 @@ class LocalPart:
     push_peer: np.ndarray      # (nOwned,4) index into `peers`, -1 unused
     push_row: np.ndarray       # (nOwned,4) ghost row index on that peer
     recv_rows: dict            # peer rank -> slice of local ghost rows filled by that peer
+    push_rank: np.ndarray = None   # (nOwned,4) push_peer as ranks instead of indices into `peers` (Poisson halo)
 
 
 def ghost_list(nbr, owner, rank):
@@ -55,9 +56,14 @@ def partition(mt: MeshTables, owner, rank, local_order=None):
     nbr = mt.nbr[owned]
     lnbr = np.where(nbr >= 0, g2l[np.maximum(nbr, 0)], -1).astype(np.int32)
     assert not np.any((nbr >= 0) & (lnbr < 0))
+    gnb = mt.nbr[ghost] if nG else np.zeros((0, 4), np.int64)
+    ghost_nbr = np.where(gnb >= 0, g2l[np.maximum(gnb, 0)], -1).astype(np.int32)
     local = MeshTables(nbr=lnbr, area=mt.area[owned], volume=mt.volume[owned], normal=mt.normal[owned],
                        entity=mt.entity[owned], tetCentroid=mt.tetCentroid[owned],
-                       faceCentroid=mt.faceCentroid[owned], nGhost=nG, periodic=list(mt.periodic))
+                       faceCentroid=mt.faceCentroid[owned], nGhost=nG, periodic=list(mt.periodic),
+                       globalTets=nT, globalId=np.concatenate([owned, ghost]).astype(np.int32), ghostNbr=ghost_nbr,
+                       ghostArea=mt.area[ghost], ghostNormal=mt.normal[ghost], ghostTetCentroid=mt.tetCentroid[ghost],
+                       ghostFaceCentroid=mt.faceCentroid[ghost])
     gowner = owner[ghost]
     # peers: ranks that own my ghosts or hold my tets as ghosts (symmetric for face adjacency)
     peers = sorted(set(int(r) for r in np.unique(gowner)))
@@ -80,8 +86,9 @@ def partition(mt: MeshTables, owner, rank, local_order=None):
         push_peer[mine_local, slot] = pi
         push_row[mine_local, slot] = rows_on_q
         fill[mine_local] += 1
+    push_rank = np.where(push_peer >= 0, np.asarray(peers + [0], np.int32)[np.maximum(push_peer, 0)], -1).astype(np.int32)
     return LocalPart(rank=rank, owned=owned, ghost=ghost, ghost_owner=gowner, tables=local, peers=peers,
-                     push_peer=push_peer, push_row=push_row, recv_rows=recv_rows)
+                     push_peer=push_peer, push_row=push_row, recv_rows=recv_rows, push_rank=push_rank)
 
 
 def rcb_owner(centroids, nparts):
