@@ -520,6 +520,16 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     hexes = tuple(args.hexes)
+    if args.scaling == "strong":
+        # the whole C4 box (56^3 hexes = 1,053,696 tets) divided over the ranks; fits from 4 GPUs up
+        from vlasovtucker_b200 import partition as part_
+        grid = part_.rank_grid(world)
+        if any(g % r for g, r in zip(args.global_hexes, grid)):
+            raise SystemExit("--global-hexes must be divisible by the rank grid")
+        hexes = tuple(g // r for g, r in zip(args.global_hexes, grid))
+        need = 2 * 6 * hexes[0] * hexes[1] * hexes[2] * args.nv ** 3 * 8
+        if need > 170e9:
+            raise SystemExit(f"strong scaling: {need / 1e9:.0f} GB of state per GPU does not fit (use >= 4 GPUs for the C4 box)")
     nv = args.nv
     cfg = c4_setup(hexes, nv)
     tucker_cpu = None
@@ -609,27 +619,41 @@ def run_gpu(args):
     # ---- the whole loop body of Solver::Solve (solver.cpp:91-133) on the same mesh: charge density,
     # Poisson solve (periodic, pinned row, Jacobi-PCG to 2.2e-16), step — reported beside the metric
     coupled = None
-    if world == 1 and not args.no_coupled:
+    if not args.no_coupled:
         try:
-            ctx.poisson_setup(np.full((nT, 4), vtb.QBC["Periodic"], np.uint8))
+            if runner is not None:
+                from vlasovtucker_b200 import multigpu
+                multigpu.PartitionedPoisson(ctx, runner.lp, dist, np.full((nT, 4), vtb.QBC["Periodic"], np.uint8),
+                                            any_dirichlet=False)
+            else:
+                ctx.poisson_setup(np.full((nT, 4), vtb.QBC["Periodic"], np.uint8))
             bg = np.full(nT, -cfg["charge"] * cfg["dens"])
-            for _ in range(2):
+
+            def loop_body():
                 ctx.charge_density([sp], bg)
                 ctx.poisson_solve(download=False)
-                ctx.step_full(sp, dt)
-            ctx.sync()
+                step()
+
+            for _ in range(2):
+                loop_body()
+            barrier()
             nc = max(3, args.steps // 4)
             t0 = time.perf_counter()
             for _ in range(nc):
-                ctx.charge_density([sp], bg)
-                ctx.poisson_solve(download=False)
-                ctx.step_full(sp, dt)
-            ctx.sync()
+                loop_body()
+            barrier()
             loop_ms = (time.perf_counter() - t0) * 1e3 / nc
+            if dist is not None:
+                t = torch.tensor([loop_ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                loop_ms = float(t.item())
             its, res = ctx.poisson_stats()
             coupled = {"ms_per_iteration": loop_ms, "poisson_ms": loop_ms - ms_per_step, "pcg_iterations": int(its),
-                       "pcg_rel_residual": float(res), "iterations_timed": nc,
-                       "what": "vt_charge_density + vt_poisson_solve (fields stay on the device) + vt_step_full"}
+                       "pcg_rel_residual": float(res), "iterations_timed": nc, "rows": nT * world,
+                       "ratio_to_step_alone": loop_ms / ms_per_step,
+                       "what": "vt_charge_density + vt_poisson_solve (fields stay on the device"
+                               + (", rows partitioned like the tets, in-kernel reductions over the ranks" if world > 1 else "")
+                               + ") + vt_step_full" + (" + halo barrier" if world > 1 else "")}
         except Exception as exc:   # the headline metric must not depend on this extra
             coupled = {"error": str(exc)[:300]}
 
@@ -658,9 +682,9 @@ def run_gpu(args):
         line = {
             "metric": "cell x v-node updates/s per step (full format)", "value": value, "unit": "updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": workload_name(hexes, nv),
+                "workload": workload_name(hexes, nv) + (f" (strong scaling: the {args.global_hexes[0]}x{args.global_hexes[1]}x{args.global_hexes[2]}-hex box over {world} GPUs)" if args.scaling == "strong" else ""),
                 "tets_per_gpu": nT, "v_nodes": N, "state_bytes_per_gpu": 2 * nT * N * 8,
                 "l2_policy": "inputs larger than L2 (state is %.1f GB per copy); no flush needed" % (nT * N * 8 / 1e9),
                 "brick_hexes": list(args.brick) if not (args.pencil and world == 1) else None,
@@ -749,6 +773,9 @@ def main():
     ap.add_argument("--variant", type=int, default=64,
                     help="vt_step_config variant bits; 64 = the library's own choice (bulk-copy pipeline, upwind-select "
                          "arithmetic for 32^3), 2 = register-staged kernel")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --hexes per GPU (default); strong: --global-hexes divided over the GPUs (>= 4 GPUs for C4)")
+    ap.add_argument("--global-hexes", type=int, nargs=3, default=[56, 56, 56], help="--scaling strong: hexes of the whole box")
     ap.add_argument("--format", default="full", choices=["full", "tucker"],
                     help="full: the headline line (with a `tucker` object beside it); tucker: the C5 Tucker line alone")
     ap.add_argument("--tucker-hexes", type=int, nargs=3, default=[16, 16, 16], help="C5: hexes per GPU block")

@@ -34,6 +34,23 @@ __global__ void k_dfma(double* out, int iters)
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// FP64 tensor-core peak: mma.sync.aligned.m8n8k4 (256 FMA per warp instruction), 8 independent accumulators
+__global__ void k_dmma(double* out, int iters)
+{
+    double c[8][2];
+    for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = threadIdx.x + i;
+    const double a = 1.0000001, b = 0.9999999;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 static float timeit(void (*launch)(void*), void* arg, int n)
 {
     cudaEvent_t e0, e1;
@@ -54,6 +71,7 @@ struct RA { const double2* p; size_t n; int reps; double* out; int blocks; };
 static void launch_read(void* a) { RA* r = (RA*)a; k_read<<<r->blocks, 512>>>(r->p, r->n, r->reps, r->out); }
 struct FA { double* out; int iters; int blocks; };
 static void launch_dfma(void* a) { FA* f = (FA*)a; k_dfma<<<f->blocks, 256>>>(f->out, f->iters); }
+static void launch_dmma(void* a) { FA* f = (FA*)a; k_dmma<<<f->blocks, 256>>>(f->out, f->iters); }
 
 int main()
 {
@@ -78,6 +96,11 @@ int main()
     FA fa{out, 20000, sms * 8};
     const float ms = timeit(launch_dfma, &fa, 3);
     const double tf = 2.0 * 8 * fa.iters * (double)fa.blocks * 256 / (ms * 1e-3) / 1e12;
-    printf(", \"dfma_TFLOPs\": %.2f}\n", tf);
+    printf(", \"dfma_TFLOPs\": %.2f", tf);
+    FA fm{out, 5000, sms * 8};
+    const float msm = timeit(launch_dmma, &fm, 3);
+    // per warp and iteration: 8 mma x 256 FMA
+    const double tfm = 2.0 * 8 * 256 * fm.iters * (double)fm.blocks * (256 / 32) / (msm * 1e-3) / 1e12;
+    printf(", \"dmma_m8n8k4_TFLOPs\": %.2f}\n", tfm);
     return 0;
 }

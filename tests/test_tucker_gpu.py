@@ -230,3 +230,104 @@ def test_errors(oracle_mod):
     with pytest.raises(RuntimeError, match="boundary faces"):
         ctx.step_tucker(g, 1e-3)                         # x faces have no particle BC yet
     ctx.close()
+
+
+@pytest.mark.parametrize("eps", [1e-8, 1e-10])
+def test_step_parity_small_compression_error(oracle_mod, eps):
+    """comprErr below ~1e-7 (the class default is 1e-10, particle_data.h:49): singular values taken from
+    Gram-matrix eigenvalues alone are noise below 1e-8 |sigma|; the device refines the trailing
+    eigen-directions inside their own subspace (csrc/tucker.cu, hosvd_truncate).  Against the oracle,
+    whose rounding uses a one-sided Jacobi SVD of the unfoldings as the reference uses Eigen's SVD."""
+    m = oracle_mod.Mesh.load(mesh_path("fully_periodic_coarse.msh"), [(1, 2), (3, 4), (5, 6)])
+    n, vmin, vmax = (9, 7, 5), [-3.0, -1.0, -1.0], [3.0, 1.0, 1.0]
+    dt, mass, charge = 2e-3, 2.0, 1.0
+    f = _initial(m, n, vmin, vmax)
+    E = np.random.default_rng(4).standard_normal((m.nTets, 3))
+    ts = oracle_mod.TuckerSim(m, n, vmin, vmax, mass, charge, eps)
+    ts.set_pdf(f)
+    ctx, g, bc = _ctx(m, n, vmin, vmax, mass, charge, {}, eps)
+    ctx.tucker_set_pdf(g, f)
+    ctx.field_set(E)
+    for _ in range(3):
+        ts.update_pdf(dt, E)
+        ctx.step_tucker(g, dt)
+    fo, fg = ts.get_pdf(), ctx.tucker_get_pdf(g, f.shape[1])
+    tol = eps + 1e-10
+    assert rel_l2(fg, fo) <= tol, rel_l2(fg, fo)
+    assert rel_l2(ctx.tucker_density(g), ts.density()) <= tol
+    assert np.abs(ctx.tucker_ranks(g) - ts.ranks()).max() <= 1
+    ctx.close()
+
+
+def test_truncation_rule_resolves_tiny_singular_values():
+    """A tensor with prescribed multilinear singular values 1, 1e-3, 1e-6, 1e-9, 3e-11, 1e-13: compressing
+    at eps = 1e-10 must keep the first four in every mode (sigma_j > eps |sigma| / sqrt(3), tucker.cpp:
+    450-461) and reconstruct to ~eps, which needs singular values resolved far below the 1e-8 a Gram
+    matrix gives."""
+    import vlasovtucker_b200 as vtb
+    from vlasovtucker_b200 import synthetic
+    rng = np.random.default_rng(7)
+    n = (12, 10, 8)
+    sig = np.array([1.0, 1e-3, 1e-6, 1e-9, 3e-11, 1e-13])
+    Q = [np.linalg.qr(rng.standard_normal((n[k], 6)))[0] for k in range(3)]
+    core = np.zeros((6, 6, 6))
+    for j in range(6):
+        core[j, j, j] = sig[j]          # superdiagonal core: mode-k singular values are exactly sig
+    X = np.einsum("ijk,ai,bj,ck->abc", core, Q[0], Q[1], Q[2])
+    mt = synthetic.periodic_kuhn_tables(1, 1, 1)
+    ctx = vtb.Context(0)
+    ctx.mesh_upload(mt)
+    g = ctx.species_create(n, [-1, -1, -1], [1, 1, 1], 1.0, 1.0)
+    ctx.set_face_bc(g, np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8))
+    ctx.tucker_enable(g, 1e-10, 0)
+    f = np.tile(X.ravel(order="F"), (mt.nTets, 1))
+    ctx.tucker_set_pdf(g, f)                      # exact (precision 0)
+    ctx.field_set(np.zeros((mt.nTets, 3)))
+    ctx.step_tucker(g, 0.0)                       # dt = 0: the state is only re-rounded at eps = 1e-10
+    r = ctx.tucker_ranks(g)
+    assert (r == 4).all(), r
+    out = ctx.tucker_get_pdf(g, f.shape[1])
+    assert rel_l2(out, f) <= 1e-10
+    ctx.close()
+
+
+def test_gram_dfma_and_dmma_agree(oracle_mod):
+    """The Gram matrices of the rounding come from the FP64 tensor cores (mma.sync m8n8k4, the default) or
+    from DFMA (VT_TUCKER_GRAM=dfma); both must give the same step within rounding.  Run as two child
+    processes because the switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import vlasovtucker_b200 as vtb
+from vlasovtucker_b200 import synthetic
+mt = synthetic.periodic_kuhn_tables(2, 1, 1)
+n = (20, 13, 9)
+ax = [np.linspace(-3, 3, k) for k in n]
+V0, V1, V2 = np.meshgrid(*ax, indexing="ij")
+x = mt.tetCentroid[:, 0]
+f = np.stack([((1 + 0.3 * np.sin(3 * xx)) * np.exp(-((V0 - 0.5 * np.cos(2 * xx)) ** 2 + V1 ** 2 + (V2 + 0.2) ** 2) / 2)).ravel(order="F") for xx in x])
+ctx = vtb.Context(0)
+ctx.mesh_upload(mt)
+g = ctx.species_create(n, [-3, -3, -3], [3, 3, 3], 1.0, 1.5)
+ctx.set_face_bc(g, np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8))
+ctx.tucker_enable(g, 1e-6, 0)
+ctx.tucker_set_pdf(g, f)
+ctx.field_set(0.3 * np.random.default_rng(1).standard_normal((mt.nTets, 3)))
+for _ in range(3):
+    ctx.step_tucker(g, 2e-3)
+np.save(sys.argv[1], ctx.tucker_get_pdf(g, f.shape[1]))
+''' % ROOT
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for mode in ("dmma", "dfma"):
+            path = os.path.join(td, mode + ".npy")
+            env = dict(os.environ, VT_TUCKER_GRAM=mode)
+            r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(np.load(path))
+    assert rel_l2(outs[0], outs[1]) <= 1e-9

@@ -174,8 +174,10 @@ PI = 3.14159265358979323846
     ("fully_periodic_coarse.msh", [(1, 2), (3, 4), (5, 6)], {}, 2),          # pinned row 0 on one rank
     ("rectangle_fine.msh", [(3, 4), (5, 6)], {1: ("Neumann", 0, 75.0), 2: ("Dirichlet", 0.5, 0)}, 4),
 ])
-def test_virtual_ranks_poisson(vt, oracle_mod, mesh, pairs, spec, world):
+@pytest.mark.timeout(300)
+def test_virtual_ranks_poisson(vt, oracle_mod, monkeypatch, mesh, pairs, spec, world):
     from conftest import poisson_bc_arrays
+    monkeypatch.setenv("VT_COMM_TIMEOUT_MS", "5000")   # a rank that never arrives fails the test in seconds
     from vlasovtucker_b200 import multigpu, partition as part
     m = oracle_mod.Mesh.load(mesh_path(mesh), pairs)
     mt = tables_from_oracle(m)
@@ -213,12 +215,14 @@ def test_virtual_ranks_poisson(vt, oracle_mod, mesh, pairs, spec, world):
     one.close()
 
 
-def test_virtual_ranks_coupled_loop(vt, oracle_mod):
+@pytest.mark.timeout(300)
+def test_virtual_ranks_coupled_loop(vt, oracle_mod, monkeypatch):
     """The whole loop body of Solver::Solve (solver.cpp:91-133) on three virtual ranks — charge density,
     partitioned Poisson solve, partitioned step with fused halo — against one context and the oracle
     (config C1s)."""
     from conftest import poisson_bc_arrays
     from vlasovtucker_b200 import multigpu, partition as part
+    monkeypatch.setenv("VT_COMM_TIMEOUT_MS", "5000")
     m = oracle_mod.Mesh.load(mesh_path("rectangle.msh"), [(1, 2), (3, 4), (5, 6)])
     mt = tables_from_oracle(m)
     n, vmin, vmax, q, dt, steps, world = (11, 11, 11), [-3, -.1, -.1], [3, .1, .1], 2.975e-5, 1e-4, 20, 3

@@ -78,6 +78,7 @@ struct PoissonData {
     int32_t* pushRow = nullptr;    // ... and the ghost row there
     uint32_t* epochDev = nullptr;  // reduction epoch counter, lives on the device across solves
     uint32_t barEpoch = 0;
+    unsigned long long timeoutNs = 20000000000ULL;   // 20 s; VT_COMM_TIMEOUT_MS
     std::vector<void*> ipcOpened;
     double tol = std::numeric_limits<double>::epsilon();
     int gridBlocks = 0;
@@ -86,6 +87,13 @@ struct PoissonData {
 };
 
 namespace {
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 const double kEps0 = 8.85e-12;  // constants.h:10
 constexpr int kMaxRanks = 64;
@@ -143,6 +151,7 @@ struct PcgParams {
     double* red;                  // own reduction slots
     uint32_t* flagR;
     uint32_t* epoch;
+    unsigned long long timeoutNs; // a rank that does not arrive within this time is given up on (status[1] = 1)
 };
 
 __device__ __forceinline__ double block_sum(double v, double* sh)
@@ -200,10 +209,23 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, const PcgParams&
                 asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.comm->flagR[q] + par * kMaxRanks + P.rank), "r"(epoch)
                              : "memory");
             }
-            const uint32_t* in = P.flagR + par * kMaxRanks + q;
+            uint32_t* in = P.flagR + par * kMaxRanks + q;
             uint32_t v;
+            const unsigned long long t0 = global_ns();
             do {
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(in) : "memory");
+                // CTA 0 gives up on a rank that does not arrive (a dead peer, or virtual ranks whose kernels
+                // were not scheduled side by side): it fills the slot with NaN itself, which releases the
+                // other CTAs with the same (poisoned) sum, ends the iteration and is reported by the host
+                if (blockIdx.x == 0 && (int32_t)(v - epoch) < 0 &&
+                    (P.status[1] != 0 || global_ns() - t0 > P.timeoutNs)) {
+                    double* mine = P.red + ((size_t)par * kMaxRanks + q) * 2;
+                    mine[0] = mine[1] = __longlong_as_double(0x7ff8000000000000LL);
+                    P.status[1] = 1;
+                    __threadfence();
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(in), "r"(epoch) : "memory");
+                    break;
+                }
             } while ((int32_t)(v - epoch) < 0);
         }
         __syncthreads();
@@ -280,14 +302,14 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
             if (COMM) *P.epoch = epoch;
         }
     };
-    if (rhsNorm2 == 0.0) {
+    if (!(rhsNorm2 > 0.0)) {   // zero right-hand side (Eigen returns x = 0), or a poisoned sum
         for (int i = tid; i < nAll; i += nth) P.x[i] = 0.0;
         residualNorm2 = 0.0;
         finish(0);
         return;
     }
     const double threshold = fmax(P.tol * P.tol * rhsNorm2, 2.2250738585072014e-308);
-    if (residualNorm2 < threshold) {
+    if (!(residualNorm2 >= threshold)) {
         finish(0);
         return;
     }
@@ -343,7 +365,7 @@ __global__ void __launch_bounds__(256) k_pcg(PcgParams P)
         }
         double rz;
         grid_sum2<COMM>(grid, P, epoch, l0, l1, P.partial, buf, sh, residualNorm2, rz);
-        if (residualNorm2 < threshold) break;
+        if (!(residualNorm2 >= threshold)) break;   // converged — or poisoned by a rank that never arrived
         beta = rz / absNew;
         absNew = rz;
         double* t = pc;
@@ -369,7 +391,8 @@ __global__ void k_push_vals(int n, int k, const double* __restrict__ src, const 
 }
 
 // partitioned solve: barrier over all ranks on the context stream (after the pushes above)
-__global__ void k_comm_barrier(const CommTable* comm, uint32_t* myFlags, int rank, int world, uint32_t epoch)
+__global__ void k_comm_barrier(const CommTable* comm, uint32_t* myFlags, int rank, int world, uint32_t epoch,
+                               int* status, unsigned long long timeoutNs)
 {
     const int q = threadIdx.x;
     if (q >= world || q == rank) return;
@@ -377,8 +400,13 @@ __global__ void k_comm_barrier(const CommTable* comm, uint32_t* myFlags, int ran
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(comm->flagB[q] + rank), "r"(epoch) : "memory");
     const uint32_t* in = myFlags + q;
     uint32_t v;
+    const unsigned long long t0 = global_ns();
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(in) : "memory");
+        if ((int32_t)(v - epoch) < 0 && (status[1] != 0 || global_ns() - t0 > timeoutNs)) {
+            status[1] = 1;   // reported by vt_poisson_stats / vt_sync
+            break;
+        }
     } while ((int32_t)(v - epoch) < 0);
     __threadfence_system();
 }
@@ -558,6 +586,9 @@ void read_stats(vt_ctx* ctx, PoissonData& P)
     P.lastIterations = st[0];
     P.lastRelResidual = sd[1] > 0 ? std::sqrt(sd[0] / sd[1]) : 0.0;
     P.statsPending = false;
+    if (st[1] != 0)
+        throw std::runtime_error("partitioned Poisson solve: a rank did not reach a reduction or barrier in time "
+                                 "(VT_COMM_TIMEOUT_MS); the fields of this step are invalid");
 }
 
 // Launches the solve and returns: nothing here waits for the device (a partitioned solve driven by
@@ -593,6 +624,7 @@ void run_pcg(vt_ctx* ctx, PoissonData& P, bool useGuess)
     pp.red = P.red;
     pp.flagR = P.flagR;
     pp.epoch = P.epochDev;
+    pp.timeoutNs = P.timeoutNs;
     void* args[] = {&pp};
     int blocks = std::min(P.gridBlocks, std::max(1, (P.nTot + 255) / 256));
     const bool comm = P.commWorld > 1;
@@ -613,7 +645,7 @@ void push_and_barrier(vt_ctx* ctx, PoissonData& P, const double* src, int k, boo
     double* const* base = grad ? ct->grad : ct->x;   // device addresses of the pointer arrays inside the table
     k_push_vals<<<(P.n + 127) / 128, 128, 0, ctx->stream>>>(P.n, k, src, P.pushRank, P.pushRow, base);
     P.barEpoch++;
-    k_comm_barrier<<<1, kMaxRanks, 0, ctx->stream>>>(ct, P.flagB, P.commRank, P.commWorld, P.barEpoch);
+    k_comm_barrier<<<1, kMaxRanks, 0, ctx->stream>>>(ct, P.flagB, P.commRank, P.commWorld, P.barEpoch, P.status, P.timeoutNs);
     ctx->launches += 2;
     VT_CUDA(cudaGetLastError());
 }
@@ -857,6 +889,25 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
         P.gridBlocks = std::max(1, std::min(perSm, 2) * ctx->prop.multiProcessorCount);
         VT_CUDA(cudaMalloc(&P.partial, 4 * (size_t)P.gridBlocks * sizeof(double)));
         VT_CUDA(cudaMalloc(&P.status, 2 * sizeof(int)));
+        VT_CUDA(cudaMemset(P.status, 0, 2 * sizeof(int)));
+        if (const char* t = std::getenv("VT_COMM_TIMEOUT_MS")) P.timeoutNs = (unsigned long long)std::atoll(t) * 1000000ULL;
+        // ... and every kernel of the solve path has to be resident in the context before the first solve:
+        // with lazy module loading the first launch of a kernel loads it, which can wait for running
+        // kernels — such as another rank's solve that is itself waiting for this rank
+        {
+            cudaFuncAttributes fa;
+            VT_CUDA(cudaFuncGetAttributes(&fa, k_pcg<true>));
+            VT_CUDA(cudaFuncGetAttributes(&fa, k_pcg<false>));
+            VT_CUDA(cudaFuncGetAttributes(&fa, k_rhs));
+            VT_CUDA(cudaFuncGetAttributes(&fa, k_correct));
+            VT_CUDA(cudaFuncGetAttributes(&fa, k_gradient));
+            VT_CUDA(cudaFuncGetAttributes(&fa, k_push_vals));
+            VT_CUDA(cudaFuncGetAttributes(&fa, k_comm_barrier));
+        }
+        // nothing may be allocated once solves are in flight: an allocation (device or page-locked host
+        // memory) is a device-wide synchronisation point, and a rank whose kernels wait for another rank
+        // of the same process would then wait forever
+        (void)ctx_pinned(ctx, 4 * nA * sizeof(double));
         VT_CUDA(cudaMalloc(&P.statusD, 2 * sizeof(double)));
         P.haveGradient = false;
         return 0;

@@ -265,6 +265,208 @@ __device__ void gram_mode(const double* __restrict__ X, const int d[3], int mode
     __syncthreads();
 }
 
+// ---- the same three Gram matrices on the FP64 tensor cores: mma.sync.aligned.m8n8k4.f64 (SASS DMMA),
+// 256 FMA per warp instruction.  G = T T^T over shared-memory tiles T: for an 8-row block B and four
+// consecutive contraction indices k0..k0+3 a lane l holds the "fragment" T[8B + l/4][k0 + l%4] — as the A
+// operand for block row I and, unchanged, as the B operand for block column J — so one shared load per
+// lane feeds a whole 8x8x4 product, against 1.25 loads per FMA in the DFMA version above.  Tiles are
+// stored with a leading dimension == 4 (mod 16), which makes both fragment walks (along and across the
+// leading dimension) bank-conflict free, and are zero padded to multiples of 8 / 4.  The upper
+// triangle of 8x8 blocks is dealt out to the warps (a block pair stays with one warp for the whole
+// accumulation, so nothing is reduced across warps): slabs X(:,:,i2) feed modes 0 and 1 at once (half
+// of the warps each), row chunks of the M x n2 matrix feed mode 2.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+__host__ __device__ constexpr int pad_ld(int n)   // smallest ld >= roundup(n, 8) with ld % 16 == 4
+{
+    const int p = (n + 7) / 8 * 8;
+    return p + ((4 - p % 16) + 16) % 16;
+}
+// 16-byte asynchronous copy global -> shared
+__device__ __forceinline__ void cp_async16(double* dst, const double* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+// PP = block pairs a warp may own (compile-time bound of the accumulator array)
+// doubles per staging tile buffer: the DFMA Gram / mode-product layouts or the zero-padded DMMA tiles
+__host__ __device__ constexpr int tile_cap(int nmax)
+{
+    const int a = ((nmax | 1) > (nmax + kQB - 1) / kQB * kQB ? (nmax | 1) : (nmax + kQB - 1) / kQB * kQB) * nmax;
+    const int b = pad_ld(nmax) * ((nmax + 7) / 8 * 8);
+    return a > b ? a : b;
+}
+
+template <int T, int NM>
+struct DmmaPairs {
+    static constexpr int nb = (NM + 7) / 8;
+    static constexpr int pairs = nb * (nb + 1) / 2;
+    static constexpr int warps = T / 32;
+    static constexpr int perHalf = (pairs + warps / 2 - 1) / (warps / 2);   // slab pass: half of the warps per mode
+    static constexpr int perAll = (pairs + warps - 1) / warps;              // chunk pass: all warps on mode 2
+};
+
+// Block pair (I, J), I <= J, has the index p = I + J(J+1)/2 and belongs to warp p % NGW of its group,
+// where it is accumulator p / NGW: all of this is resolved at compile time inside fully unrolled
+// loops, so fragments and accumulators stay in registers (the only run-time test is the warp-uniform
+// "is this pair mine").
+// Accumulate `nk` contraction steps of 4 from one tile.  alongLd == false: the Gram index runs along
+// the contiguous direction of the tile (fragment T[(8B+g) + ld*(k0+c)]); true: across it
+// (fragment T[(k0+c) + ld*(8B+g)]).
+template <int NB, int NGW, int PP>
+__device__ __forceinline__ void dmma_tile(const double* tile, int ld, bool alongLd, int nk, int nbUsed, int wm,
+                                          double (&acc)[PP][2])
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const int rowStride = alongLd ? ld : 1, kStride = alongLd ? 1 : ld;
+    const double* base = tile + g * rowStride + c * kStride;
+    for (int k = 0; k < nk; k++) {
+        double frag[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) frag[b] = b < nbUsed ? base[(8 * b) * rowStride + (4 * k) * kStride] : 0.0;
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+#pragma unroll
+            for (int I = 0; I <= J; I++) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int p = I + J * (J + 1) / 2;
+                if (p % NGW == wm && J < nbUsed) dmma884(acc[p / NGW], frag[I], frag[J]);
+            }
+        }
+    }
+}
+
+template <int NB, int NGW, int PP>
+__device__ __forceinline__ void dmma_store(double* G, int n, int nbUsed, int wm, const double (&acc)[PP][2])
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+    const int ldg = n | 1;
+#pragma unroll
+    for (int J = 0; J < NB; J++) {
+#pragma unroll
+        for (int I = 0; I <= J; I++) {
+            const int p = I + J * (J + 1) / 2;
+            if (p % NGW != wm || J >= nbUsed) continue;
+            const int i = 8 * I + g;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int j = 8 * J + 2 * c + u;
+                if (i < n && j < n) {
+                    G[i + ldg * j] = acc[p / NGW][u];
+                    G[j + ldg * i] = acc[p / NGW][u];   // diagonal blocks write both triangles from the exact same sums
+                }
+            }
+        }
+    }
+}
+
+template <int T, int NM>
+__device__ void gram_all_dmma(const double* __restrict__ X, const int d[3], double* const G[3], const GramWork& gw)
+{
+    using DP = DmmaPairs<T, NM>;
+    constexpr int NB = DP::nb;
+    const int warp = threadIdx.x >> 5;
+    constexpr int W = T / 32, HW = W / 2;
+    const int n0 = d[0], n1 = d[1], n2 = d[2], M = n0 * n1;
+    double* tile0 = gw.tile;
+    double* tile1 = gw.tile + gw.tileCap;
+    auto zero_tiles = [&]() {
+        for (int e = threadIdx.x; e < 2 * gw.tileCap; e += T) gw.tile[e] = 0.0;
+        __syncthreads();
+    };
+    // ---- pass A: slabs, modes 0 and 1
+    {
+        const int mode = warp < HW ? 0 : 1;
+        const int wm = warp < HW ? warp : warp - HW;
+        const int n = d[mode], nb = (n + 7) / 8;
+        double acc[DP::perHalf][2];
+#pragma unroll
+        for (int q = 0; q < DP::perHalf; q++) acc[q][0] = acc[q][1] = 0.0;
+        const int ld = pad_ld(n0);
+        zero_tiles();
+        const bool vec2 = (n0 % 2 == 0) && ((reinterpret_cast<size_t>(X) & 15) == 0);
+        auto issue = [&](int i2) {
+            const double* slab = X + (size_t)i2 * M;
+            double* t = (i2 & 1) ? tile1 : tile0;
+            if (vec2) {
+                const int h0 = n0 / 2;
+                for (int e = threadIdx.x; e < M / 2; e += T) cp_async16(t + 2 * (e % h0) + ld * (e / h0), slab + 2 * e);
+            } else {
+                for (int e = threadIdx.x; e < M; e += T) cp_async8(t + (e % n0) + ld * (e / n0), slab + e);
+            }
+            cp_async_commit();
+        };
+        const int nk = mode == 0 ? (n1 + 3) / 4 : (n0 + 3) / 4;
+        issue(0);
+        for (int i2 = 0; i2 < n2; i2++) {
+            if (i2 + 1 < n2) {
+                issue(i2 + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            dmma_tile<NB, HW, DP::perHalf>((i2 & 1) ? tile1 : tile0, ld, mode == 1, nk, nb, wm, acc);
+            __syncthreads();
+        }
+        dmma_store<NB, HW, DP::perHalf>(G[mode], n, nb, wm, acc);
+    }
+    // ---- pass B: X as an M x n2 matrix, row chunks, mode 2
+    {
+        const int n = n2, nb = (n + 7) / 8;
+        double acc[DP::perAll][2];
+#pragma unroll
+        for (int q = 0; q < DP::perAll; q++) acc[q][0] = acc[q][1] = 0.0;
+        // chunk of `rows` consecutive rows: tile[r + ld * a], ld == 4 (mod 16), 8*nb columns
+        int ld = gw.tileCap / (8 * nb);
+        ld -= ((ld % 16) - 4 + 16) % 16;
+        const int rows = ld / 4 * 4;
+        const int nChunks = (M + rows - 1) / rows;
+        zero_tiles();
+        const bool vec2 = (M % 2 == 0) && (rows % 2 == 0) && ((reinterpret_cast<size_t>(X) & 15) == 0);
+        auto issue = [&](int cidx) {
+            const int r0 = cidx * rows, nr = min(rows, M - r0);
+            double* t = (cidx & 1) ? tile1 : tile0;
+            if (nr < rows) {   // the last chunk is short: clear what the chunk before it left behind
+                for (int e = threadIdx.x; e < (rows - nr) * n2; e += T) t[nr + e % (rows - nr) + ld * (e / (rows - nr))] = 0.0;
+            }
+            if (vec2 && nr % 2 == 0) {
+                const int h = nr / 2;
+                for (int e = threadIdx.x; e < h * n2; e += T) {
+                    const int r = 2 * (e % h), a = e / h;
+                    cp_async16(t + r + ld * a, X + (size_t)r0 + r + (size_t)M * a);
+                }
+            } else {
+                for (int e = threadIdx.x; e < nr * n2; e += T) {
+                    const int r = e % nr, a = e / nr;
+                    cp_async8(t + r + ld * a, X + (size_t)r0 + r + (size_t)M * a);
+                }
+            }
+            cp_async_commit();
+        };
+        issue(0);
+        for (int cidx = 0; cidx < nChunks; cidx++) {
+            if (cidx + 1 < nChunks) {
+                issue(cidx + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const int nr = min(rows, M - cidx * rows);
+            dmma_tile<NB, W, DP::perAll>((cidx & 1) ? tile1 : tile0, ld, true, (nr + 3) / 4, nb, warp, acc);
+            __syncthreads();
+        }
+        dmma_store<NB, W, DP::perAll>(G[2], n, nb, warp, acc);
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ double wsum(double v)
 {
 #pragma unroll
@@ -495,6 +697,11 @@ struct TruncWork {
     int* order;       // [3][kMaxN] shared: descending order
     int* rsel;        // [3] shared: selected ranks
     GramWork gw;
+    bool dmma;        // Gram matrices on the FP64 tensor cores (gram_all_dmma) instead of DFMA (gram_mode)
+    double* refV;     // global, 2 x kMaxN^2: sorted eigenvectors / rotated trailing block (small-eps refinement)
+    double* trInv;    // [3] shared: 1 / trace of each Gram matrix
+    int* misc;        // [4] shared: scratch integers of the refinement
+    double* sorted;   // [kMaxN] shared: eigenvalues in descending order (refinement)
     long long* prof;  // optional phase timers (thread 0 of CTA 0): gram, eig, select, project, reconstruct, flux, derivative
 };
 
@@ -506,7 +713,9 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
                                double* coreOut, double* W1, double* W2, const TruncWork& w)
 {
     long long t0 = clock64();
-    for (int k = 0; k < 3; k++) gram_mode<T, NM>(X, d, k, w.G[k], w.gw);
+    if (w.dmma) gram_all_dmma<T, NM>(X, d, w.G, w.gw);
+    else
+        for (int k = 0; k < 3; k++) gram_mode<T, NM>(X, d, k, w.G[k], w.gw);
     long long t1 = clock64();
     if (w.prof) w.prof[0] += t1 - t0;
     const int warp = threadIdx.x >> 5;
@@ -523,6 +732,7 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
             for (int j = 0; j < n; j++)
                 for (int i = lane; i < n; i += 32) G[i + ld * j] *= inv;
         }
+        if (lane == 0) w.trInv[warp] = tr > 0.0 ? 1.0 / tr : 0.0;
         __syncwarp();
     }
     if (warp < 3) eig_sym_warp(w.G[warp], d[warp], d[warp] | 1, w.dv + warp * kMaxN, w.ev + warp * kMaxN);
@@ -540,6 +750,100 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
         w.order[k * kMaxN + rank] = j;
     }
     __syncthreads();
+    // ---- small compression errors.  Eigenvalues of a Gram matrix carry an absolute error of ~1e-16 of
+    // the trace, i.e. singular values below ~1e-8 |sigma| are noise, while the rank rule compares them
+    // with eps |sigma| / sqrt(3) (tucker.cpp:450-461; the class default is eps = 1e-10,
+    // particle_data.h:49).  When the threshold is that low, the trailing eigen-directions (lambda <
+    // 1e-12 of the trace) are resolved a second time inside their own subspace: Y = V_s^T X_(k), Gram
+    // matrix of Y, eigen-decomposition W, V_s <- V_s W.  Relative to ITS largest value that small
+    // problem is again good to 1e-8, so singular values are trustworthy down to ~1e-14 |sigma|.
+    {
+        bool refine = eps > 0.0 ? (eps * eps / 3.0 < 1e-13) : false;
+        if (eps == 0.0)
+            for (int k = 0; k < 3; k++)
+                if (min(rmax, rcap[k]) < d[k]) refine = true;   // precision 0 with a binding rank cap: the order matters
+        if (refine) {
+            for (int k = 0; k < 3; k++) {
+                const int n = d[k], ld = n | 1;
+                double* lam = w.dv + k * kMaxN;
+                int* ord = w.order + k * kMaxN;
+                if (threadIdx.x == 0) {
+                    int m = 0;
+                    while (m < n && lam[ord[m]] >= 1e-12) m++;
+                    w.misc[0] = m;
+                }
+                __syncthreads();
+                const int m = w.misc[0], sN = n - m;
+                if (sN == 0) continue;
+                double* Vs = w.refV;                        // n x n, sorted columns
+                double* Rt = w.refV + (size_t)kMaxN * kMaxN;   // n x sN rotated trailing block
+                for (int p = threadIdx.x; p < n * n; p += blockDim.x) Vs[p] = w.G[k][(p % n) + ld * ord[p / n]];
+                for (int j = threadIdx.x; j < n; j += blockDim.x) w.sorted[j] = lam[ord[j]];   // sorted eigenvalues
+                __syncthreads();
+                // Y = X x_k V_s^T  (mode-k dimension sN)
+                int dd[3] = {d[0], d[1], d[2]};
+                mode_apply(X, W1, dd, k, Vs + (size_t)n * m, n, sN, true, w.gw.tile);
+                dd[k] = sN;
+                gram_mode<T, NM>(W1, dd, k, w.G[k], w.gw);   // sN x sN, leading dimension sN | 1
+                const int lds = sN | 1;
+                if (threadIdx.x < 32) {
+                    const int lane = threadIdx.x;
+                    double tr = 0.0;
+                    for (int i = lane; i < sN; i += 32) tr += w.G[k][i + lds * i];
+                    tr = wsum(tr);
+                    const double inv = tr > 0.0 ? 1.0 / tr : 0.0;
+                    for (int j = 0; j < sN; j++)
+                        for (int i = lane; i < sN; i += 32) w.G[k][i + lds * j] *= inv;
+                    __syncwarp();
+                    if (tr > 0.0) eig_sym_warp(w.G[k], sN, lds, lam, w.ev + k * kMaxN);
+                    __syncwarp();
+                    if (lane == 0) {
+                        // descending order of the sN values (insertion sort), scaled back to the unit-trace units of lam
+                        const double scale = tr * w.trInv[k];
+                        for (int j = 0; j < sN; j++) ord[j] = j;
+                        if (tr > 0.0)
+                            for (int a = 1; a < sN; a++) {
+                                const int key = ord[a];
+                                int b = a - 1;
+                                while (b >= 0 && lam[ord[b]] < lam[key]) {
+                                    ord[b + 1] = ord[b];
+                                    b--;
+                                }
+                                ord[b + 1] = key;
+                            }
+                        w.misc[1] = tr > 0.0 ? 1 : 0;
+                        for (int j = 0; j < sN; j++) lam[j] = fmax(lam[j], 0.0) * scale;
+                    }
+                }
+                __syncthreads();
+                const bool rotated = w.misc[1] != 0;
+                // rotated trailing vectors: Rt(:, j) = sum_q Vs(:, m+q) W(q, ord[j])
+                for (int p = threadIdx.x; p < n * sN; p += blockDim.x) {
+                    const int i = p % n, j = p / n;
+                    double acc = 0.0;
+                    if (rotated)
+                        for (int q = 0; q < sN; q++) acc = fma(Vs[i + (size_t)n * (m + q)], w.G[k][q + lds * ord[j]], acc);
+                    else acc = Vs[i + (size_t)n * (m + j)];
+                    Rt[p] = acc;
+                }
+                __syncthreads();
+                // reassemble: sorted leading part, refined trailing part; eigenvalues and order follow
+                if (threadIdx.x == 0) {
+                    double tmp[kMaxN];
+                    for (int j = 0; j < sN; j++) tmp[j] = rotated ? lam[ord[j]] : w.sorted[m + j];
+                    for (int j = 0; j < m; j++) lam[j] = w.sorted[j];
+                    for (int j = 0; j < sN; j++) lam[m + j] = tmp[j];
+                }
+                __syncthreads();
+                for (int p = threadIdx.x; p < n * n; p += blockDim.x) {
+                    const int i = p % n, j = p / n;
+                    w.G[k][i + ld * j] = j < m ? Vs[p] : Rt[i + (size_t)n * (j - m)];
+                }
+                for (int j = threadIdx.x; j < n; j += blockDim.x) ord[j] = j;
+                __syncthreads();
+            }
+        }
+    }
     if (threadIdx.x < 3) {
         const int k = threadIdx.x, n = d[k];
         const double* lam = w.dv + k * kMaxN;
@@ -624,6 +928,7 @@ struct TuckerParams {
     int mode;                // 0 step, 1 compress dense input, 2 reconstruct, 3 |v.n| tables
     double epsAbs;           // mode 3: compression error for |v.n| (rank cap 6)
     long long* prof;         // optional: 8 phase timers in clock cycles (VT_TUCKER_PROFILE)
+    int gramDmma;            // 1: Gram matrices by mma.sync f64 (the default), 0: DFMA (VT_TUCKER_GRAM=dfma)
     double* peerOut[kMaxPeers];   // multi-GPU: peers' state buffers receiving the ghost copies
     int* peerRout[kMaxPeers];
 };
@@ -654,8 +959,14 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
     w.ev = sEv;
     w.order = sOrder;
     w.rsel = sR;
+    __shared__ double sTrInv[3], sSorted[kMaxN];
+    __shared__ int sMisc[4];
+    w.trInv = sTrInv;
+    w.misc = sMisc;
+    w.sorted = sSorted;
     w.gw.tile = sDyn + (size_t)3 * matElems;
-    w.gw.tileCap = max(nmaxS | 1, (nmaxS + kQB - 1) / kQB * kQB) * nmaxS;   // also stages a padded factor (mode_apply)
+    w.gw.tileCap = tile_cap(nmaxS);   // also stages a padded factor (mode_apply) and the padded DMMA tiles
+    w.dmma = P.gramDmma != 0;
     w.gw.groups = sGroups;
     w.gw.nmax = nmaxS;
     build_groups(sGroups, nmaxS);
@@ -674,6 +985,7 @@ __global__ void __launch_bounds__(T, T == kThreads ? 2 : 4) k_tucker(const Tucke
     double* W2 = W1 + N;
     double* Uw[3] = {W2 + N, W2 + N + (size_t)kMaxN * kMaxN, W2 + N + 2 * (size_t)kMaxN * kMaxN};   // factors of intermediates
     double* coreW = Uw[2] + (size_t)kMaxN * kMaxN;                                                  // [N]
+    w.refV = coreW + N;                                                                             // 2 x kMaxN^2: small-eps refinement
     const int fullcap[3] = {d[0], d[1], d[2]};
 
     for (int t = blockIdx.x; t < P.nOwned; t += gridDim.x) {
@@ -903,11 +1215,15 @@ void fill_params(vt_ctx* ctx, Species& sp, TuckerState& ts, TuckerParams& P)
     P.density = sp.density;
     P.wall = sp.wall;
     P.scratch = ts.scratch;
-    P.scratchPerCTA = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
+    P.scratchPerCTA = (size_t)6 * sp.N + 5 * (size_t)kMaxN * kMaxN;
     P.qm = sp.charge / sp.mass;
     P.cellVolume = sp.cellVolume;
     P.eps = ts.comprErr;
     P.maxRank = ts.maxRank;
+    // Gram matrices on the FP64 tensor cores unless VT_TUCKER_GRAM=dfma asks for the DFMA version
+    // (both kept: profiles/ holds an ncu summary of each)
+    static const bool dfma = std::getenv("VT_TUCKER_GRAM") && std::string(std::getenv("VT_TUCKER_GRAM")) == "dfma";
+    P.gramDmma = dfma ? 0 : 1;
 }
 
 void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
@@ -915,7 +1231,7 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     if (ctx->nOwned == 0) return;
     const int grid = std::min(ctx->nOwned, ts.scratchCTAs);
     const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
-    const size_t smem = (3 * (size_t)(nmax | 1) + 2 * std::max(nmax | 1, (nmax + kQB - 1) / kQB * kQB)) * nmax * sizeof(double);
+    const size_t smem = (3 * (size_t)(nmax | 1) * nmax + 2 * (size_t)tile_cap(nmax)) * sizeof(double);
     if (nmax <= 16) {
         k_tucker<kThreadsSmall, 16><<<grid, kThreadsSmall, smem, ctx->stream>>>(P);
     } else if (nmax <= 32) {
@@ -925,7 +1241,7 @@ void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
     } else {
         if (smem > 32 * 1024)
             VT_CUDA(cudaFuncSetAttribute(k_tucker<kThreads, kMaxN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         5 * (kMaxN | 1) * kMaxN * (int)sizeof(double)));
+                                         (int)((3 * (size_t)(kMaxN | 1) * kMaxN + 2 * (size_t)tile_cap(kMaxN)) * sizeof(double))));
         k_tucker<kThreads, kMaxN><<<grid, kThreads, smem, ctx->stream>>>(P);
     }
     ctx->launches++;
@@ -1062,7 +1378,7 @@ int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
         VT_CUDA(cudaMalloc(&ts->vnabs, nA * 4 * ts->vslot * sizeof(double)));
         VT_CUDA(cudaMalloc(&ts->vnabsRanks, nA * 12 * sizeof(int)));
         ts->scratchCTAs = (nmax <= 32 ? 4 : 2) * ctx->prop.multiProcessorCount;
-        const size_t per = (size_t)6 * sp.N + 3 * (size_t)kMaxN * kMaxN;
+        const size_t per = (size_t)6 * sp.N + 5 * (size_t)kMaxN * kMaxN;
         VT_CUDA(cudaMalloc(&ts->scratch, (size_t)ts->scratchCTAs * per * sizeof(double)));
         tucker_from_dense(ctx, sp);   // whatever the species holds (zeros after vt_species_create)
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
