@@ -1,5 +1,8 @@
-"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): the partitioned update with
-the halo exchange fused into the step kernel reproduces the single-GPU update bit for bit."""
+"""Multi-GPU parity, one process per GPU under torchrun (CUDA-IPC peer mappings): the partitioned update
+with the halo exchange fused into the step kernel reproduces the single-GPU update bit for bit, the
+coupled loop with the partitioned Poisson solve matches one GPU.  On a box with a single GPU the same
+partitions, kernels, push lists and device-side barriers run as virtual ranks of one process
+(tests/test_virtual_ranks_gpu.py) — the tests below then run that form instead of being skipped."""
 import os
 import subprocess
 import sys
@@ -11,12 +14,20 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
+def _virtual(test_name, *args):
+    """One GPU: the virtual-rank form of the same check."""
+    import vlasovtucker_b200 as vtb
+    import test_virtual_ranks_gpu as tv
+    vtb.capi.load()
+    getattr(tv, test_name)(vtb, *args)
+
+
 @pytest.mark.parametrize("variant", ["0", "2", "18"])
 def test_partitioned_update_bit_identical(variant):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
-        pytest.skip("needs >= 2 GPUs")
+        return _virtual("test_virtual_ranks_full_bit_identical", 2, "rcb", (16, 8, 8), 2, int(variant))
     world = 4 if n >= 4 else 2
     env = dict(os.environ, VT_VARIANT=variant)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
@@ -26,12 +37,12 @@ def test_partitioned_update_bit_identical(variant):
     assert "MGPU_CHECK_OK" in r.stdout
 
 
-def test_partitioned_coupled_loop():
-    """Density -> replicated Poisson -> partitioned step -> wall charge over ranks, against one GPU."""
+def test_partitioned_coupled_loop(oracle_mod, monkeypatch):
+    """Density -> partitioned Poisson -> partitioned step -> wall charge over ranks, against one GPU."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
-        pytest.skip("needs >= 2 GPUs")
+        return _virtual("test_virtual_ranks_coupled_loop", oracle_mod, monkeypatch)
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "mgpu_loop_check.py")]
@@ -45,7 +56,7 @@ def test_partitioned_tucker_bit_identical():
     import torch
     n = torch.cuda.device_count()
     if n < 2:
-        pytest.skip("needs >= 2 GPUs")
+        return _virtual("test_virtual_ranks_tucker_bit_identical")
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29521", os.path.join(ROOT, "scripts", "mgpu_tucker_check.py")]

@@ -753,23 +753,30 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
     // ---- small compression errors.  Eigenvalues of a Gram matrix carry an absolute error of ~1e-16 of
     // the trace, i.e. singular values below ~1e-8 |sigma| are noise, while the rank rule compares them
     // with eps |sigma| / sqrt(3) (tucker.cpp:450-461; the class default is eps = 1e-10,
-    // particle_data.h:49).  When the threshold is that low, the trailing eigen-directions (lambda <
-    // 1e-12 of the trace) are resolved a second time inside their own subspace: Y = V_s^T X_(k), Gram
-    // matrix of Y, eigen-decomposition W, V_s <- V_s W.  Relative to ITS largest value that small
-    // problem is again good to 1e-8, so singular values are trustworthy down to ~1e-14 |sigma|.
+    // particle_data.h:49).  When the threshold is that low, the trailing eigen-directions are resolved
+    // a second time inside their own subspace: Y = V_s^T X_(k), Gram matrix of Y, eigen-decomposition
+    // W, V_s <- V_s W.  The cut between "leading" and "trailing" sits at sigma = 1e-4 |sigma| (lambda =
+    // 1e-8 of the trace): a leading direction leaks into the computed trailing vectors with an amplitude
+    // of ~1e-16 / lambda, i.e. it pollutes the trailing singular values by 1e-16 / sigma <= 1e-12, and
+    // inside the block (largest value 1e-4) the Gram eigenvalues are again good to 1e-8 of that, so
+    // singular values come out with ~1e-12 |sigma| of noise — enough for eps >= ~1e-11.  Below that
+    // (and for precision 0 with a binding rank cap) a second pass resolves the block sigma < 1e-8 the
+    // same way, which brings the noise to ~1e-16.
     {
         bool refine = eps > 0.0 ? (eps * eps / 3.0 < 1e-13) : false;
         if (eps == 0.0)
             for (int k = 0; k < 3; k++)
                 if (min(rmax, rcap[k]) < d[k]) refine = true;   // precision 0 with a binding rank cap: the order matters
-        if (refine) {
+        const int nPass = !refine ? 0 : ((eps == 0.0 || eps < 1e-11) ? 2 : 1);
+        for (int pass = 0; pass < nPass; pass++) {
+            const double cut = pass == 0 ? 1e-8 : 1e-16;
             for (int k = 0; k < 3; k++) {
                 const int n = d[k], ld = n | 1;
                 double* lam = w.dv + k * kMaxN;
                 int* ord = w.order + k * kMaxN;
                 if (threadIdx.x == 0) {
                     int m = 0;
-                    while (m < n && lam[ord[m]] >= 1e-12) m++;
+                    while (m < n && lam[ord[m]] >= cut) m++;
                     w.misc[0] = m;
                 }
                 __syncthreads();
@@ -1220,10 +1227,15 @@ void fill_params(vt_ctx* ctx, Species& sp, TuckerState& ts, TuckerParams& P)
     P.cellVolume = sp.cellVolume;
     P.eps = ts.comprErr;
     P.maxRank = ts.maxRank;
-    // Gram matrices on the FP64 tensor cores unless VT_TUCKER_GRAM=dfma asks for the DFMA version
-    // (both kept: profiles/ holds an ncu summary of each)
-    static const bool dfma = std::getenv("VT_TUCKER_GRAM") && std::string(std::getenv("VT_TUCKER_GRAM")) == "dfma";
-    P.gramDmma = dfma ? 0 : 1;
+    // Gram matrices: FP64 tensor cores (mma.sync m8n8k4) or DFMA.  Measured on B200 (profiles/
+    // r2_tucker_gram_dmma_vs_dfma.md): the two pipes have the same peak (37.0 vs 35.0 TFLOP/s), and the
+    // tensor-core version wins where the operand traffic from shared memory dominates — 11^3: 4.8 vs 5.3
+    // ms, 32^3: 36.9 vs 44.8 ms per step — and loses at 48^3 (32.5 vs 29.4 ms), where the DFMA version's
+    // register blocking already amortises the loads.  Default: tensor cores up to 32 nodes per axis;
+    // VT_TUCKER_GRAM=dmma|dfma forces either.
+    static const char* mode = std::getenv("VT_TUCKER_GRAM");
+    const int nmax = std::max({sp.n[0], sp.n[1], sp.n[2]});
+    P.gramDmma = mode ? (std::string(mode) == "dmma" ? 1 : 0) : (nmax <= 32 ? 1 : 0);
 }
 
 void launch(vt_ctx* ctx, TuckerState& ts, const TuckerParams& P)
