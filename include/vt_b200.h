@@ -40,6 +40,16 @@ int vt_version(void);
 
 /* ---- context ------------------------------------------------------------------------------ */
 int vt_ctx_create(int device, vt_ctx** out);
+/* One context that drives several GPUs from one host thread (devices may repeat: "virtual ranks" on
+ * one GPU).  The group partitions the mesh of vt_mesh_upload over its members (contiguous chunks of
+ * the locality order), wires their ghost rows directly to each other and translates every per-tet
+ * call below into calls on the members; per step it runs exactly what the one-process-per-GPU path
+ * runs (fused halo push, device-side barriers, partitioned Poisson solve).  This is how the C++ host
+ * classes use all GPUs of a box (VT_DEVICES=0,1,...; the reference's Solver<T>::Solve,
+ * src/solver.cpp:80-138, is single-process).  The vt_halo_*, vt_poisson_comm_*, vt_profile_* and
+ * vt_step_full_host entry points apply to single-device contexts only. */
+int vt_ctx_create_group(const int* devices, int nDevices, vt_ctx** out);
+int vt_group_size(vt_ctx* ctx);
 void vt_ctx_destroy(vt_ctx* ctx);
 int vt_sync(vt_ctx* ctx);
 /* device properties the bench reports (SM count, L2 bytes, HBM bytes) */

@@ -21,6 +21,8 @@ SIGNATURES = {
     "vt_last_error": (C.c_char_p, []),
     "vt_version": (C.c_int, []),
     "vt_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "vt_ctx_create_group": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "vt_group_size": (C.c_int, [C.c_void_p]),
     "vt_ctx_destroy": (None, [C.c_void_p]),
     "vt_sync": (C.c_int, [C.c_void_p]),
     "vt_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

@@ -46,9 +46,15 @@ class MeshTables:
 
 class Context:
     def __init__(self, device=0):
+        """device: an index, or a list of indices for a device group (vt_ctx_create_group; entries may
+        repeat = virtual ranks on one GPU)."""
         self.lib = capi.load()
         h = C.c_void_p()
-        capi.check(self.lib.vt_ctx_create(int(device), C.byref(h)))
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*[int(d) for d in device])
+            capi.check(self.lib.vt_ctx_create_group(arr, len(device), C.byref(h)))
+        else:
+            capi.check(self.lib.vt_ctx_create(int(device), C.byref(h)))
         self.h = h
         self.nOwned = 0
         self.grids = []

@@ -100,6 +100,7 @@ extern "C" {
 
 int vt_halo_export(vt_ctx* ctx, int species, void* handles)
 {
+    if (ctx->group) { vt_set_error("vt_halo_export: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -114,6 +115,7 @@ int vt_halo_export(vt_ctx* ctx, int species, void* handles)
 
 int vt_halo_attach(vt_ctx* ctx, int species, int myRank, int nPeers, const int32_t* peerRanks, const void* peerHandles)
 {
+    if (ctx->group) { vt_set_error("vt_halo_attach: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -146,6 +148,7 @@ int vt_halo_attach(vt_ctx* ctx, int species, int myRank, int nPeers, const int32
 int vt_halo_attach_local(vt_ctx* ctx, int species, int myRank, int nPeers, const int32_t* peerRanks,
                          vt_ctx* const* peerCtx, const int32_t* peerSpecies)
 {
+    if (ctx->group) { vt_set_error("vt_halo_attach_local: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -183,6 +186,7 @@ int vt_halo_attach_local(vt_ctx* ctx, int species, int myRank, int nPeers, const
 
 int vt_halo_set_push(vt_ctx* ctx, int species, const int32_t* pushPeer, const int32_t* pushRow)
 {
+    if (ctx->group) { vt_set_error("vt_halo_set_push: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -197,6 +201,7 @@ int vt_halo_set_push(vt_ctx* ctx, int species, const int32_t* pushPeer, const in
 
 int vt_halo_push_current(vt_ctx* ctx, int species)
 {
+    if (ctx->group) { vt_set_error("vt_halo_push_current: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -218,6 +223,7 @@ int vt_halo_push_current(vt_ctx* ctx, int species)
 
 int vt_halo_barrier(vt_ctx* ctx)
 {
+    if (ctx->group) { vt_set_error("vt_halo_barrier: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (ctx->nPeers == 0) return;

@@ -686,6 +686,7 @@ extern "C" {
 int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceCentroid, const uint8_t* bcType,
                      const double* bcValue, const double* bcNormalGrad)
 {
+    if (ctx->group) return vt::group_poisson_setup(ctx, tetCentroid, faceCentroid, bcType, bcValue, bcNormalGrad);
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (ctx->nGhost > 0 && ctx->globalId.empty())
@@ -952,6 +953,7 @@ int vt_poisson_set_global_dirichlet(vt_ctx* ctx, int anyDirichlet)
 
 int vt_poisson_comm_export(vt_ctx* ctx, void* handle)
 {
+    if (ctx->group) { vt_set_error("vt_poisson_comm_export: not available on a device group"); return 1; };
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
@@ -969,6 +971,7 @@ int vt_poisson_comm_export(vt_ctx* ctx, void* handle)
 
 int vt_poisson_comm_attach(vt_ctx* ctx, int myRank, int world, const void* handles)
 {
+    if (ctx->group) { vt_set_error("vt_poisson_comm_attach: not available on a device group"); return 1; };
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
@@ -999,6 +1002,7 @@ int vt_poisson_comm_attach(vt_ctx* ctx, int myRank, int world, const void* handl
 
 int vt_poisson_comm_attach_local(vt_ctx* ctx, int myRank, int world, vt_ctx* const* ranks)
 {
+    if (ctx->group) { vt_set_error("vt_poisson_comm_attach_local: not available on a device group"); return 1; };
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
@@ -1035,6 +1039,7 @@ int vt_poisson_comm_attach_local(vt_ctx* ctx, int myRank, int world, vt_ctx* con
 
 int vt_poisson_set_push(vt_ctx* ctx, const int32_t* pushRank, const int32_t* pushRow)
 {
+    if (ctx->group) { vt_set_error("vt_poisson_set_push: not available on a device group"); return 1; };
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
@@ -1066,6 +1071,7 @@ int vt_poisson_set_push(vt_ctx* ctx, const int32_t* pushRank, const int32_t* pus
 
 int vt_poisson_update_bc_values(vt_ctx* ctx, const double* bcValue, const double* bcNormalGrad)
 {
+    if (ctx->group) return vt::group_poisson_update_bc_values(ctx, bcValue, bcNormalGrad);
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
@@ -1080,6 +1086,7 @@ int vt_poisson_update_bc_values(vt_ctx* ctx, const double* bcValue, const double
 
 int vt_poisson_solve(vt_ctx* ctx, const double* rho, double* phi, double* E)
 {
+    if (ctx->group) return vt::group_poisson_solve(ctx, rho, phi, E);
     try {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->poisson) throw std::runtime_error("vt_poisson_setup has not been called");
@@ -1128,6 +1135,7 @@ int vt_poisson_solve(vt_ctx* ctx, const double* rho, double* phi, double* E)
 
 int vt_poisson_stats(vt_ctx* ctx, int* lastIterations, double* lastRelResidual)
 {
+    if (ctx->group) return vt::group_poisson_stats(ctx, lastIterations, lastRelResidual);
     if (!ctx->poisson) return 1;
     try {
         VT_CUDA(cudaSetDevice(ctx->device));

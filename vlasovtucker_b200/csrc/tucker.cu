@@ -861,9 +861,14 @@ __device__ void hosvd_truncate(const double* X, const int d[3], double eps, int 
         const double thr = eps * sqrt(s2) / sqrt(3.0);
         int r = 0;
         const int cap = min(rmax, rcap[k]);
+        // precision 0 ("exact", particle_data.cpp:64-69): the reference keeps every sigma_j > 0, and an SVD
+        // returns tiny positive values for the numerically-zero ones, i.e. everything is kept; here a
+        // numerically-zero Gram eigenvalue may come out <= 0, which must not cut the prefix short (a
+        // component of 1e-9 |sigma| has lambda = 1e-18, far below the eigenvalue noise)
+        const bool keepAll = eps == 0.0 && s2 > 0.0;
         for (int j = 0; j < n; j++) {
             const double sig = sqrt(fmax(lam[ord[j]], 0.0));
-            if (r == 0 || (sig > thr && r < cap)) r++;   // sorted: a prefix is kept       (tucker.cpp:454-460)
+            if (r == 0 || ((keepAll || sig > thr) && r < cap)) r++;   // sorted: a prefix is kept       (tucker.cpp:454-460)
             else break;
         }
         w.rsel[k] = r;
@@ -1360,6 +1365,7 @@ extern "C" {
 
 int vt_tucker_enable(vt_ctx* ctx, int species, double comprErr, int maxRank)
 {
+    if (ctx->group) return vt::group_tucker_enable(ctx, species, comprErr, maxRank);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1407,6 +1413,7 @@ static_assert(sizeof(TuckerIpc) == 128, "Tucker halo handle is 128 bytes");
 
 int vt_tucker_halo_export(vt_ctx* ctx, int species, void* handle)
 {
+    if (ctx->group) { vt_set_error("vt_tucker_halo_export: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1422,6 +1429,7 @@ int vt_tucker_halo_export(vt_ctx* ctx, int species, void* handle)
 
 int vt_tucker_halo_attach(vt_ctx* ctx, int species, int nPeers, const void* peerHandles)
 {
+    if (ctx->group) { vt_set_error("vt_tucker_halo_attach: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1441,6 +1449,7 @@ int vt_tucker_halo_attach(vt_ctx* ctx, int species, int nPeers, const void* peer
 
 int vt_tucker_halo_attach_local(vt_ctx* ctx, int species, int nPeers, vt_ctx* const* peerCtx, const int32_t* peerSpecies)
 {
+    if (ctx->group) { vt_set_error("vt_tucker_halo_attach_local: not available on a device group"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1457,6 +1466,7 @@ int vt_tucker_halo_attach_local(vt_ctx* ctx, int species, int nPeers, vt_ctx* co
 
 int vt_tucker_set_pdf(vt_ctx* ctx, int species, const double* dense)
 {
+    if (ctx->group) return vt::group_species_set_pdf(ctx, species, 0, ctx->nOwned, dense);
     // vt_species_set_pdf re-compresses a Tucker species after the upload
     if (!ctx || species < 0 || species >= (int)ctx->species.size() || !ctx->species[species]->tucker) {
         vt_set_error("species is not in Tucker format (vt_tucker_enable)");
@@ -1467,6 +1477,7 @@ int vt_tucker_set_pdf(vt_ctx* ctx, int species, const double* dense)
 
 int vt_tucker_get_pdf(vt_ctx* ctx, int species, double* dense)
 {
+    if (ctx->group) return vt::group_species_get_pdf(ctx, species, 0, ctx->nOwned, dense);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1483,6 +1494,7 @@ int vt_tucker_get_pdf(vt_ctx* ctx, int species, double* dense)
 
 int vt_tucker_get_ranks(vt_ctx* ctx, int species, int32_t* ranks)
 {
+    if (ctx->group) return vt::group_tucker_get_ranks(ctx, species, ranks);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1498,6 +1510,7 @@ int vt_tucker_get_ranks(vt_ctx* ctx, int species, int32_t* ranks)
 int vt_tucker_get_factors(vt_ctx* ctx, int species, int tet, int32_t ranks[3], double* core, double* u0, double* u1,
                           double* u2)
 {
+    if (ctx->group) return vt::group_tucker_get_factors(ctx, species, tet, ranks, core, u0, u1, u2);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1522,6 +1535,7 @@ int vt_tucker_get_factors(vt_ctx* ctx, int species, int tet, int32_t ranks[3], d
 
 int vt_tucker_density(vt_ctx* ctx, int species, double* density)
 {
+    if (ctx->group) return vt::group_species_density(ctx, species, density);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
@@ -1540,6 +1554,7 @@ int vt_tucker_density(vt_ctx* ctx, int species, double* density)
 
 int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
 {
+    if (ctx->group) return vt::group_step(ctx, species, dt, ext, true);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);

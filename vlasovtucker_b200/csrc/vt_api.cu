@@ -277,6 +277,11 @@ int vt_ctx_create(int device, vt_ctx** out)
 void vt_ctx_destroy(vt_ctx* ctx)
 {
     if (!ctx) return;
+    if (ctx->group) {
+        vt::group_destroy(ctx->group);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto* sp : ctx->species) {
@@ -312,6 +317,7 @@ void vt_ctx_destroy(vt_ctx* ctx)
 
 int vt_sync(vt_ctx* ctx)
 {
+    if (ctx->group) return vt::group_sync(ctx);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -334,6 +340,7 @@ int vt_device_info(vt_ctx* ctx, int* sm_count, size_t* l2_bytes, size_t* hbm_byt
 int vt_mesh_upload(vt_ctx* ctx, int nOwned, int nGhost, const int32_t* nbr, const double* area,
                    const double* volume, const double* normal, const int32_t* entity, const int32_t* order)
 {
+    if (ctx->group) return vt::group_mesh_upload(ctx, nOwned, nGhost, nbr, area, volume, normal, entity, order);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (nOwned < 0 || nGhost < 0) throw std::invalid_argument("negative tet count");
@@ -379,6 +386,7 @@ int vt_mesh_set_ghost_geometry(vt_ctx* ctx, int globalTets, const int32_t* globa
                                const double* ghostArea, const double* ghostNormal, const double* ghostTetCentroid,
                                const double* ghostFaceCentroid)
 {
+    if (ctx->group) { vt_set_error("vt_mesh_set_ghost_geometry: not available on a device group (call it on a single-device context)"); return 1; };
     return guard([&] {
         const size_t nO = ctx->nOwned, nG = ctx->nGhost;
         if (globalTets < (int)nO) throw std::invalid_argument("vt_mesh_set_ghost_geometry: globalTets < nOwned");
@@ -397,6 +405,7 @@ int vt_mesh_set_ghost_geometry(vt_ctx* ctx, int globalTets, const int32_t* globa
 int vt_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], const double vmax[3], double mass,
                       double charge, int* species)
 {
+    if (ctx->group) return vt::group_species_create(ctx, n, vmin, vmax, mass, charge, species);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (n[0] < 2 || n[1] < 2 || n[2] < 2) throw std::invalid_argument("velocity grid needs >= 2 nodes per axis");
@@ -427,6 +436,7 @@ int vt_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], con
 
 int vt_species_set_params(vt_ctx* ctx, int species, double mass, double charge)
 {
+    if (ctx->group) return vt::group_species_set_params(ctx, species, mass, charge);
     return guard([&] {
         vt::Species& sp = species_of(ctx, species);
         sp.mass = mass;
@@ -437,6 +447,7 @@ int vt_species_set_params(vt_ctx* ctx, int species, double mass, double charge)
 int vt_species_set_face_bc(vt_ctx* ctx, int species, const uint8_t* bcType, const uint8_t* collect,
                            const int32_t* sourceId)
 {
+    if (ctx->group) return vt::group_species_set_face_bc(ctx, species, bcType, collect, sourceId);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -452,6 +463,7 @@ int vt_species_set_face_bc(vt_ctx* ctx, int species, const uint8_t* bcType, cons
 
 int vt_species_set_source_pdfs(vt_ctx* ctx, int species, int nSource, const double* pdf)
 {
+    if (ctx->group) return vt::group_species_set_source_pdfs(ctx, species, nSource, pdf);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -467,6 +479,7 @@ int vt_species_set_source_pdfs(vt_ctx* ctx, int species, int nSource, const doub
 
 int vt_species_set_pdf(vt_ctx* ctx, int species, int first, int count, const double* pdf)
 {
+    if (ctx->group) return vt::group_species_set_pdf(ctx, species, first, count, pdf);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -498,6 +511,7 @@ int vt_species_set_pdf(vt_ctx* ctx, int species, int first, int count, const dou
 
 int vt_species_get_pdf(vt_ctx* ctx, int species, int first, int count, double* pdf)
 {
+    if (ctx->group) return vt::group_species_get_pdf(ctx, species, first, count, pdf);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -527,6 +541,7 @@ int vt_species_get_pdf(vt_ctx* ctx, int species, int first, int count, double* p
 int vt_species_set_maxwell(vt_ctx* ctx, int species, const double* physDensity, double temperature,
                            const double mpv[3])
 {
+    if (ctx->group) return vt::group_species_set_maxwell(ctx, species, physDensity, temperature, mpv);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -583,6 +598,7 @@ int vt_species_set_maxwell(vt_ctx* ctx, int species, const double* physDensity, 
 int vt_species_set_separable(vt_ctx* ctx, int species, int nTerms, const double* amp, const double* a0,
                              const double* a1, const double* a2)
 {
+    if (ctx->group) { vt_set_error("vt_species_set_separable: not available on a device group (call it on a single-device context)"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -613,6 +629,7 @@ int vt_species_set_separable(vt_ctx* ctx, int species, int nTerms, const double*
 
 int vt_measure_dfma_peak(vt_ctx* ctx, double* tflops)
 {
+    if (ctx->group) { vt_set_error("vt_measure_dfma_peak: not available on a device group (call it on a single-device context)"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         const int blocks = 8 * ctx->prop.multiProcessorCount, threads = 256, iters = 20000;
@@ -640,6 +657,7 @@ int vt_measure_dfma_peak(vt_ctx* ctx, double* tflops)
 
 int vt_species_density(vt_ctx* ctx, int species, double* density)
 {
+    if (ctx->group) return vt::group_species_density(ctx, species, density);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -650,6 +668,7 @@ int vt_species_density(vt_ctx* ctx, int species, double* density)
 
 int vt_species_velocity(vt_ctx* ctx, int species, double* velocity)
 {
+    if (ctx->group) return vt::group_species_velocity(ctx, species, velocity);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -670,6 +689,7 @@ int vt_species_velocity(vt_ctx* ctx, int species, double* velocity)
 
 int vt_field_set(vt_ctx* ctx, const double* E)
 {
+    if (ctx->group) return vt::group_field_set(ctx, E);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         upload_tet_array(ctx, E, ctx->E, 3);
@@ -678,6 +698,7 @@ int vt_field_set(vt_ctx* ctx, const double* E)
 
 int vt_field_get(vt_ctx* ctx, double* rho, double* phi, double* E)
 {
+    if (ctx->group) return vt::group_field_get(ctx, rho, phi, E);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (rho) download_tet_array(ctx, ctx->rho, rho, 1);
@@ -688,6 +709,7 @@ int vt_field_get(vt_ctx* ctx, double* rho, double* phi, double* E)
 
 int vt_step_full(vt_ctx* ctx, int species, double dt, const double ext[3])
 {
+    if (ctx->group) return vt::group_step(ctx, species, dt, ext, false);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::launch_full_step(ctx, species_of(ctx, species), dt, ext);
@@ -696,6 +718,7 @@ int vt_step_full(vt_ctx* ctx, int species, double dt, const double ext[3])
 
 int vt_step_full_host(vt_ctx* ctx, int species, double dt, const double ext[3], const double* E, double* density)
 {
+    if (ctx->group) { vt_set_error("vt_step_full_host: not available on a device group (call it on a single-device context)"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -727,6 +750,7 @@ int vt_step_config(vt_ctx* ctx, int chunkPlanes, int brickTets, int variant)
 
 int vt_step_last_ms(vt_ctx* ctx, float* ms)
 {
+    if (ctx->group) { vt_set_error("vt_step_last_ms: not available on a device group (call it on a single-device context)"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         VT_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -734,10 +758,11 @@ int vt_step_last_ms(vt_ctx* ctx, float* ms)
     });
 }
 
-long vt_launch_count(vt_ctx* ctx) { return ctx->launches; }
+long vt_launch_count(vt_ctx* ctx) { return ctx->group ? vt::group_launch_count(ctx) : ctx->launches; }
 
 int vt_profile_begin(vt_ctx* ctx)
 {
+    if (ctx->group) { vt_set_error("vt_profile_begin: not available on a device group (call it on a single-device context)"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->regionStart) {
@@ -753,6 +778,7 @@ int vt_profile_begin(vt_ctx* ctx)
 
 int vt_profile_end(vt_ctx* ctx, float* region_ms, float* step_kernel_ms, int* step_kernels)
 {
+    if (ctx->group) { vt_set_error("vt_profile_end: not available on a device group (call it on a single-device context)"); return 1; };
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (!ctx->profiling) throw std::runtime_error("vt_profile_end without vt_profile_begin");
@@ -775,6 +801,7 @@ int vt_profile_end(vt_ctx* ctx, float* region_ms, float* step_kernel_ms, int* st
 
 int vt_wall_charge_get(vt_ctx* ctx, int species, int entity, double* charge)
 {
+    if (ctx->group) return vt::group_wall_charge_get(ctx, species, entity, charge);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -789,6 +816,7 @@ int vt_wall_charge_get(vt_ctx* ctx, int species, int entity, double* charge)
 
 int vt_wall_charge_reset(vt_ctx* ctx, int species)
 {
+    if (ctx->group) return vt::group_wall_charge_reset(ctx, species);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         vt::Species& sp = species_of(ctx, species);
@@ -798,6 +826,7 @@ int vt_wall_charge_reset(vt_ctx* ctx, int species)
 
 int vt_charge_density(vt_ctx* ctx, const int* species, int nSpecies, const double* background)
 {
+    if (ctx->group) return vt::group_charge_density(ctx, species, nSpecies, background);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         const int n = ctx->nOwned;

@@ -91,6 +91,7 @@ struct Species {
 };
 
 struct PoissonData;
+struct Group;
 void tucker_destroy(TuckerState* ts);
 
 }  // namespace vt
@@ -139,6 +140,7 @@ struct vt_ctx {
     unsigned long long* workCounter = nullptr;   // device: heads of the persistent kernels' work queues (2)
 
     vt::PoissonData* poisson = nullptr;
+    vt::Group* group = nullptr;   // device group (vt_ctx_create_group): this context only dispatches to its members
 
     // multi-GPU: flag words for the device-side barrier between steps (CUDA-IPC shared)
     int rank = 0, nPeers = 0;
@@ -154,6 +156,37 @@ struct vt_ctx {
 extern "C" void vt_set_error(const char* msg);   // internal: sets vt_last_error()
 
 namespace vt {
+// device groups (group.cu): the C ABI entry points hand a group context over to these
+void group_destroy(Group* g);
+int group_mesh_upload(vt_ctx* ctx, int nTets, int nGhost, const int32_t* nbr, const double* area, const double* volume,
+                      const double* normal, const int32_t* entity, const int32_t* order);
+int group_species_create(vt_ctx* ctx, const int32_t n[3], const double vmin[3], const double vmax[3], double mass,
+                         double charge, int* species);
+int group_species_set_params(vt_ctx* ctx, int sp, double mass, double charge);
+int group_species_set_face_bc(vt_ctx* ctx, int sp, const uint8_t* bcType, const uint8_t* collect, const int32_t* sourceId);
+int group_species_set_source_pdfs(vt_ctx* ctx, int sp, int nSource, const double* pdf);
+int group_species_set_pdf(vt_ctx* ctx, int sp, int first, int count, const double* pdf);
+int group_species_get_pdf(vt_ctx* ctx, int sp, int first, int count, double* pdf);
+int group_species_set_maxwell(vt_ctx* ctx, int sp, const double* physDensity, double temperature, const double mpv[3]);
+int group_species_density(vt_ctx* ctx, int sp, double* density);
+int group_species_velocity(vt_ctx* ctx, int sp, double* velocity);
+int group_field_set(vt_ctx* ctx, const double* E);
+int group_field_get(vt_ctx* ctx, double* rho, double* phi, double* E);
+int group_step(vt_ctx* ctx, int sp, double dt, const double ext[3], bool tucker);
+int group_wall_charge_get(vt_ctx* ctx, int sp, int entity, double* charge);
+int group_wall_charge_reset(vt_ctx* ctx, int sp);
+int group_charge_density(vt_ctx* ctx, const int* species, int nSpecies, const double* background);
+int group_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceCentroid, const uint8_t* bcType,
+                        const double* bcValue, const double* bcNormalGrad);
+int group_poisson_update_bc_values(vt_ctx* ctx, const double* bcValue, const double* bcNormalGrad);
+int group_poisson_solve(vt_ctx* ctx, const double* rho, double* phi, double* E);
+int group_poisson_stats(vt_ctx* ctx, int* its, double* res);
+int group_tucker_enable(vt_ctx* ctx, int sp, double comprErr, int maxRank);
+int group_tucker_get_factors(vt_ctx* ctx, int sp, int tet, int32_t ranks[3], double* core, double* u0, double* u1, double* u2);
+int group_tucker_get_ranks(vt_ctx* ctx, int sp, int32_t* ranks);
+int group_sync(vt_ctx* ctx);
+long group_launch_count(vt_ctx* ctx);
+
 void launch_full_step(vt_ctx* ctx, Species& sp, double dt, const double ext[3]);
 void launch_density(vt_ctx* ctx, Species& sp);
 // Tucker species: refresh the dense copy of the state in sp.f[sp.cur] (no-op when current)
