@@ -2,6 +2,7 @@
 // The per-step exchange itself is fused into the step kernel (full_step.cu, HALO path).
 #include "vt_internal.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -28,7 +29,7 @@ __global__ void k_push_rows(const double* __restrict__ f, const vt::TetRec* __re
 // All ranks announce `epoch` in every peer's flag array, then wait for every peer's announcement.
 // Stream order guarantees the step kernel (and its peer stores) finished before this runs.
 __global__ void k_halo_barrier(uint32_t* myFlags, uint32_t* const* peerFlags, const int* peerRank, int nPeers,
-                               int myRank, uint32_t epoch, int* status)
+                               int myRank, uint32_t epoch, volatile int* status, unsigned long long timeoutNs)
 {
     const int i = threadIdx.x;
     if (i >= nPeers) return;
@@ -36,12 +37,19 @@ __global__ void k_halo_barrier(uint32_t* myFlags, uint32_t* const* peerFlags, co
     volatile uint32_t* out = peerFlags[i] + myRank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(out), "r"(epoch) : "memory");
     const uint32_t* in = myFlags + peerRank[i];
-    const long long t0 = clock64();
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
     uint32_t v;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(in) : "memory");
-        if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; do not hang the GPU
-            atomicExch(status, 1);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        if ((int32_t)(v - epoch) < 0 && (*status != 0 || t - t0 > timeoutNs)) {
+            // a peer did not arrive (it died, or it is far behind): do not hang the GPU.  The flag lives
+            // in mapped host memory and is sticky: every later vt_step_* / vt_halo_barrier / vt_sync of
+            // this context fails instead of computing with ghost rows that may be stale.
+            *status = 1;
+            __threadfence_system();
             break;
         }
     } while ((int32_t)(v - epoch) < 0);
@@ -59,8 +67,11 @@ void ensure_flags(vt_ctx* ctx)
     if (ctx->flags) return;
     VT_CUDA(cudaMalloc(&ctx->flags, 64 * sizeof(uint32_t)));
     VT_CUDA(cudaMemset(ctx->flags, 0, 64 * sizeof(uint32_t)));
-    VT_CUDA(cudaMalloc(&ctx->haloStatus, sizeof(int)));
-    VT_CUDA(cudaMemset(ctx->haloStatus, 0, sizeof(int)));
+    // the barrier's time-out flag: mapped host memory, so the host sees it without synchronising
+    VT_CUDA(cudaHostAlloc(&ctx->haloStatusHost, sizeof(int), cudaHostAllocMapped));
+    *ctx->haloStatusHost = 0;
+    VT_CUDA(cudaHostGetDevicePointer(&ctx->haloStatus, ctx->haloStatusHost, 0));
+    if (const char* t = std::getenv("VT_COMM_TIMEOUT_MS")) ctx->haloTimeoutNs = (unsigned long long)std::atoll(t) * 1000000ULL;
 }
 
 // the barrier kernel reads the peers' flag pointers and ranks from a small device table
@@ -94,6 +105,12 @@ int guard(F f)
 
 namespace vt {
 void rebuild_tet_records_public(vt_ctx* ctx, Species& sp);
+void check_halo_status(vt_ctx* ctx)
+{
+    if (ctx->haloStatusHost && *static_cast<volatile int*>(ctx->haloStatusHost) != 0)
+        throw std::runtime_error("halo barrier timed out earlier: a peer rank did not reach the step barrier "
+                                 "(VT_COMM_TIMEOUT_MS); the ghost rows of this context are not trustworthy");
+}
 }
 
 extern "C" {
@@ -227,6 +244,7 @@ int vt_halo_barrier(vt_ctx* ctx)
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         if (ctx->nPeers == 0) return;
+        vt::check_halo_status(ctx);
         ctx->epoch++;
         // peer flag pointers and ranks: the device table written by vt_halo_attach(_local)
         if (!ctx->haloTable) upload_halo_table(ctx);
@@ -234,7 +252,7 @@ int vt_halo_barrier(vt_ctx* ctx)
         const int* prDev = reinterpret_cast<const int*>(reinterpret_cast<const char*>(ctx->haloTable) +
                                                         vt::kMaxPeers * sizeof(uint32_t*));
         k_halo_barrier<<<1, 32, 0, ctx->stream>>>(ctx->flags, pfDev, prDev, ctx->nPeers, ctx->rank, ctx->epoch,
-                                                  ctx->haloStatus);
+                                                  ctx->haloStatus, ctx->haloTimeoutNs);
         ctx->launches++;
         VT_CUDA(cudaGetLastError());
     });

@@ -1563,6 +1563,7 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
             throw std::runtime_error(std::to_string(sp.danglingFaces) + " boundary faces have no neighbour and no particle BC");
         if (sp.nPeers > 0 && ts.nPeers != sp.nPeers)
             throw std::runtime_error("partitioned Tucker species: vt_tucker_halo_attach has not been called");
+        check_halo_status(ctx);
         ensure_vnabs(ctx, sp, ts);
         TuckerParams P;
         fill_params(ctx, sp, ts, P);

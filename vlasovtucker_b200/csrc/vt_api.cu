@@ -159,6 +159,16 @@ void download_tet_array(vt_ctx* ctx, const double* dev, double* host, int k)
 void rebuild_tet_records(vt_ctx* ctx, vt::Species& sp)
 {
     const int n = ctx->nOwned;
+    // absorbed charge collected so far, by entity: a change of the boundary conditions (or of the halo
+    // push lists) renumbers the accumulator slots but must not lose the charge — the reference keeps
+    // _wallCharge across SetParticleBC and across Solve() calls (solver.cpp:296-311 only adds entities)
+    std::map<int, double> kept;
+    if (sp.wall && !sp.wallEntities.empty()) {
+        std::vector<double> old(sp.wallEntities.size());
+        VT_CUDA(cudaStreamSynchronize(ctx->stream));
+        VT_CUDA(cudaMemcpy(old.data(), sp.wall, old.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < old.size(); i++) kept[sp.wallEntities[i]] = old[i];
+    }
     sp.recHost.assign(n, vt::TetRec());
     sp.wallEntities.clear();
     sp.danglingFaces = 0;
@@ -215,11 +225,16 @@ void rebuild_tet_records(vt_ctx* ctx, vt::Species& sp)
     }
     if (!sp.rec) VT_CUDA(cudaMalloc(&sp.rec, std::max<size_t>(1, n) * sizeof(vt::TetRec)));
     VT_CUDA(cudaMemcpy(sp.rec, sp.recHost.data(), (size_t)n * sizeof(vt::TetRec), cudaMemcpyHostToDevice));
-    // changing the BCs restarts the wall-charge accumulators (as _InitializeWallCharge, solver.cpp:296-311)
+    // new accumulator slots; entities that keep a slot keep their charge (vt_wall_charge_reset zeroes them)
     if (sp.wall) VT_CUDA(cudaFree(sp.wall));
     sp.wall = nullptr;
-    VT_CUDA(cudaMalloc(&sp.wall, std::max<size_t>(1, sp.wallEntities.size()) * sizeof(double)));
-    VT_CUDA(cudaMemset(sp.wall, 0, std::max<size_t>(1, sp.wallEntities.size()) * sizeof(double)));
+    std::vector<double> init(std::max<size_t>(1, sp.wallEntities.size()), 0.0);
+    for (size_t i = 0; i < sp.wallEntities.size(); i++) {
+        auto it = kept.find(sp.wallEntities[i]);
+        if (it != kept.end()) init[i] = it->second;
+    }
+    VT_CUDA(cudaMalloc(&sp.wall, init.size() * sizeof(double)));
+    VT_CUDA(cudaMemcpy(sp.wall, init.data(), init.size() * sizeof(double), cudaMemcpyHostToDevice));
 }
 }  // namespace
 
@@ -298,7 +313,7 @@ void vt_ctx_destroy(vt_ctx* ctx)
     }
     for (void* p : ctx->ipcOpened) cudaIpcCloseMemHandle(p);
     cudaFree(ctx->flags);
-    cudaFree(ctx->haloStatus);
+    if (ctx->haloStatusHost) cudaFreeHost(ctx->haloStatusHost);
     cudaFree(ctx->haloTable);
     cudaFree(ctx->workCounter);
     if (ctx->poisson) vt::poisson_destroy(ctx->poisson);
@@ -321,11 +336,7 @@ int vt_sync(vt_ctx* ctx)
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->haloStatus) {
-            int st = 0;
-            VT_CUDA(cudaMemcpy(&st, ctx->haloStatus, sizeof(int), cudaMemcpyDeviceToHost));
-            if (st) throw std::runtime_error("halo barrier timed out: a peer rank did not reach the step barrier");
-        }
+        vt::check_halo_status(ctx);
     });
 }
 
@@ -345,6 +356,7 @@ int vt_mesh_upload(vt_ctx* ctx, int nOwned, int nGhost, const int32_t* nbr, cons
         VT_CUDA(cudaSetDevice(ctx->device));
         if (nOwned < 0 || nGhost < 0) throw std::invalid_argument("negative tet count");
         if (!ctx->species.empty()) throw std::runtime_error("vt_mesh_upload must precede vt_species_create");
+        if (ctx->orderDev) throw std::runtime_error("vt_mesh_upload: this context already holds a mesh (create a new context)");
         ctx->nOwned = nOwned;
         ctx->nGhost = nGhost;
         ctx->order.resize(nOwned);
@@ -712,6 +724,7 @@ int vt_step_full(vt_ctx* ctx, int species, double dt, const double ext[3])
     if (ctx->group) return vt::group_step(ctx, species, dt, ext, false);
     return guard([&] {
         VT_CUDA(cudaSetDevice(ctx->device));
+        vt::check_halo_status(ctx);
         vt::launch_full_step(ctx, species_of(ctx, species), dt, ext);
     });
 }

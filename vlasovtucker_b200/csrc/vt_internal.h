@@ -148,7 +148,9 @@ struct vt_ctx {
     uint32_t* flags = nullptr;                       // [64] one word per source rank, local
     uint32_t* peerFlags[vt::kMaxPeers] = {};         // peers' flag arrays
     uint32_t epoch = 0;
-    int* haloStatus = nullptr;                       // device: != 0 when a barrier timed out
+    int* haloStatus = nullptr;                       // device view of haloStatusHost: != 0 when a barrier timed out (sticky)
+    int* haloStatusHost = nullptr;                   // mapped host memory
+    unsigned long long haloTimeoutNs = 20000000000ULL;   // VT_COMM_TIMEOUT_MS
     std::vector<void*> ipcOpened;
     void* haloTable = nullptr;                       // device copy of the peer flag pointers/ranks
 };
@@ -196,6 +198,7 @@ void tucker_from_dense(vt_ctx* ctx, Species& sp);
 // Tucker species, multi-GPU: copy the current slots of the boundary tets into the peers' ghost rows
 void tucker_push_current(vt_ctx* ctx, Species& sp);
 void poisson_destroy(PoissonData* p);
+void check_halo_status(vt_ctx* ctx);   // throws when a halo barrier of this context has timed out
 double* ctx_stage(vt_ctx* ctx, size_t bytes);
 double* ctx_pinned(vt_ctx* ctx, size_t bytes);
 }  // namespace vt

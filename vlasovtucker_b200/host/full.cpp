@@ -32,14 +32,13 @@ Full& Full::operator=(const Full& o)
     return *this;
 }
 
-Full& Full::operator=(Full&& o) noexcept
+Full& Full::operator=(Full&& o)
 {
     if (this == &o) return *this;
     if (OnDevice()) {
-        try {
-            *this = static_cast<const Full&>(o);   // upload
-        } catch (...) {
-        }
+        // assignment to a device-resident row uploads; a shape mismatch or a CUDA failure propagates
+        // exactly as from the copy assignment (nothing is swallowed)
+        *this = static_cast<const Full&>(o);
         return *this;
     }
     _tensor = std::move(o._tensor);

@@ -27,7 +27,7 @@ public:
     Full(const Tensor3d& tensor);
     Full(Full&& other) noexcept;             // moves keep the binding (std::vector growth)
     Full(const Full& other);                 // copies materialise: the copy is a host value
-    Full& operator=(Full&& other) noexcept;
+    Full& operator=(Full&& other);   // uploads when the target is a device-resident row: may throw
     Full& operator=(const Full& other);      // into a handle: uploads the row
 
     // ---- element-wise algebra (same operator set as Tucker, so Solver<T> code is format agnostic)
