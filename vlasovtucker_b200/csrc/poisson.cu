@@ -67,8 +67,7 @@ struct PoissonData {
     int nTot = 0;                  // owned + ghost rows
     void* xchg = nullptr;
     size_t xchgBytes = 0;
-    double* red = nullptr;         // [2][kMaxRanks][2]: partial sums written by rank s, double buffered
-    uint32_t* flagR = nullptr;     // [2][kMaxRanks]: reduction epoch announced by rank s
+    unsigned long long* ll = nullptr;   // [2][kMaxRanks][4]: the ranks' partial sums as {epoch, payload} words, double buffered
     uint32_t* flagB = nullptr;     // [kMaxRanks]: barrier epoch announced by rank s
     int commRank = 0, commWorld = 1;
     void* peerXchg[64] = {};       // base of every rank's exchange block (own entry = own block)
@@ -103,22 +102,20 @@ struct CommTable {
     double* x[kMaxRanks];
     double* z[kMaxRanks];
     double* grad[kMaxRanks];
-    double* red[kMaxRanks];
-    uint32_t* flagR[kMaxRanks];
+    unsigned long long* ll[kMaxRanks];   // [2][kMaxRanks][4] words {epoch : 32, payload : 32}
     uint32_t* flagB[kMaxRanks];
 };
 
 // layout of a rank's exchange block for nTot rows
 struct XchgLayout {
-    size_t x, z, grad, red, flagR, flagB, bytes;
+    size_t x, z, grad, ll, flagB, bytes;
     explicit XchgLayout(size_t nTot)
     {
         x = 0;
         z = x + nTot * sizeof(double);
         grad = z + nTot * sizeof(double);
-        red = grad + 3 * nTot * sizeof(double);
-        flagR = red + 2 * kMaxRanks * 2 * sizeof(double);
-        flagB = flagR + 2 * kMaxRanks * sizeof(uint32_t);
+        ll = grad + 3 * nTot * sizeof(double);
+        flagB = ll + 2 * kMaxRanks * 4 * sizeof(unsigned long long);
         bytes = flagB + kMaxRanks * sizeof(uint32_t);
     }
 };
@@ -148,8 +145,7 @@ struct PcgParams {
     const CommTable* comm;
     const int32_t* pushRank;
     const int32_t* pushRow;
-    double* red;                  // own reduction slots
-    uint32_t* flagR;
+    unsigned long long* ll;       // own reduction slots
     uint32_t* epoch;
     unsigned long long timeoutNs; // a rank that does not arrive within this time is given up on (status[1] = 1)
 };
@@ -177,7 +173,8 @@ __device__ __forceinline__ double block_sum(double v, double* sh)
 // grid (the z halo) are visible to a peer once it has seen the epoch (fence + grid sync + release).
 template <bool COMM>
 __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, const PcgParams& P, uint32_t& epoch, double a, double b,
-                                          double* partial, int& buf, double* sh, double& outA, double& outB)
+                                          double* partial, int& buf, double* sh, double& outA, double& outB,
+                                          bool pushed = false)
 {
     const double sa = block_sum(a, sh);
     const double sb = block_sum(b, sh);
@@ -187,7 +184,7 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, const PcgParams&
         pb[2 * blockIdx.x] = sa;
         pb[2 * blockIdx.x + 1] = sb;
     }
-    if (COMM) __threadfence_system();
+    if (COMM && pushed) __threadfence_system();   // this thread's z halo stores are ordered before the sums below
     grid.sync();
     double ta = 0.0, tb = 0.0;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
@@ -197,36 +194,40 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, const PcgParams&
     outA = block_sum(ta, sh);
     outB = block_sum(tb, sh);
     if (COMM) {
+        // Sum over the ranks, LL style: every 8-byte word a rank stores into a peer carries 32 bits of
+        // payload and the 32-bit reduction epoch, so the word itself says when it is valid — no separate
+        // flag, no fence between data and flag on the critical path.  The two sums travel as four such
+        // words (thread 4q+h of CTA 0 stores word h into rank q).  Every CTA polls its own rank's slots and
+        // adds the ranks' values in rank order: all CTAs of all ranks end up with the same bits.  Slots are
+        // double buffered by epoch parity (a rank is at most one reduction ahead of the slowest one).
         epoch++;
         const int par = epoch & 1u;
-        const int q = threadIdx.x;
+        const int t = threadIdx.x, q = t >> 2, h = t & 3;
+        __shared__ uint32_t halves[kMaxRanks][4];
         if (q < P.world && q != P.rank) {
             if (blockIdx.x == 0) {
-                double* dst = P.comm->red[q] + ((size_t)par * kMaxRanks + P.rank) * 2;
-                dst[0] = outA;
-                dst[1] = outB;
-                __threadfence_system();
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.comm->flagR[q] + par * kMaxRanks + P.rank), "r"(epoch)
-                             : "memory");
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(h < 2 ? outA : outB);
+                const unsigned long long word = ((unsigned long long)epoch << 32) | ((h & 1) ? (bits >> 32) : (bits & 0xffffffffULL));
+                unsigned long long* dst = P.comm->ll[q] + ((size_t)par * kMaxRanks + P.rank) * 4 + h;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
             }
-            uint32_t* in = P.flagR + par * kMaxRanks + q;
-            uint32_t v;
+            unsigned long long* in = P.ll + ((size_t)par * kMaxRanks + q) * 4 + h;
+            unsigned long long v;
             const unsigned long long t0 = global_ns();
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(in) : "memory");
+            while (true) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(in) : "memory");
+                if ((uint32_t)(v >> 32) == epoch) break;
                 // CTA 0 gives up on a rank that does not arrive (a dead peer, or virtual ranks whose kernels
                 // were not scheduled side by side): it fills the slot with NaN itself, which releases the
                 // other CTAs with the same (poisoned) sum, ends the iteration and is reported by the host
-                if (blockIdx.x == 0 && (int32_t)(v - epoch) < 0 &&
-                    (P.status[1] != 0 || global_ns() - t0 > P.timeoutNs)) {
-                    double* mine = P.red + ((size_t)par * kMaxRanks + q) * 2;
-                    mine[0] = mine[1] = __longlong_as_double(0x7ff8000000000000LL);
+                if (blockIdx.x == 0 && (P.status[1] != 0 || global_ns() - t0 > P.timeoutNs)) {
+                    v = ((unsigned long long)epoch << 32) | ((h & 1) ? 0x7ff80000ULL : 0ULL);
                     P.status[1] = 1;
-                    __threadfence();
-                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(in), "r"(epoch) : "memory");
+                    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(in), "l"(v) : "memory");
                     break;
                 }
-            } while ((int32_t)(v - epoch) < 0);
+            }
+            halves[q][h] = (uint32_t)v;
         }
         __syncthreads();
         double ga = 0.0, gb = 0.0;
@@ -235,9 +236,8 @@ __device__ __forceinline__ void grid_sum2(cg::grid_group& grid, const PcgParams&
                 ga += outA;
                 gb += outB;
             } else {
-                const volatile double* src = P.red + ((size_t)par * kMaxRanks + s) * 2;
-                ga += src[0];
-                gb += src[1];
+                ga += __longlong_as_double(((long long)halves[s][1] << 32) | halves[s][0]);
+                gb += __longlong_as_double(((long long)halves[s][3] << 32) | halves[s][2]);
             }
         }
         outA = ga;
@@ -621,8 +621,7 @@ void run_pcg(vt_ctx* ctx, PoissonData& P, bool useGuess)
     pp.comm = static_cast<const CommTable*>(P.commTable);
     pp.pushRank = P.pushRank;
     pp.pushRow = P.pushRow;
-    pp.red = P.red;
-    pp.flagR = P.flagR;
+    pp.ll = P.ll;
     pp.epoch = P.epochDev;
     pp.timeoutNs = P.timeoutNs;
     void* args[] = {&pp};
@@ -880,8 +879,7 @@ int vt_poisson_setup(vt_ctx* ctx, const double* tetCentroid, const double* faceC
         P.x = reinterpret_cast<double*>(xb + lay.x);
         P.z = reinterpret_cast<double*>(xb + lay.z);
         P.grad = reinterpret_cast<double*>(xb + lay.grad);
-        P.red = reinterpret_cast<double*>(xb + lay.red);
-        P.flagR = reinterpret_cast<uint32_t*>(xb + lay.flagR);
+        P.ll = reinterpret_cast<unsigned long long*>(xb + lay.ll);
         P.flagB = reinterpret_cast<uint32_t*>(xb + lay.flagB);
         VT_CUDA(cudaMalloc(&P.epochDev, sizeof(uint32_t)));
         VT_CUDA(cudaMemset(P.epochDev, 0, sizeof(uint32_t)));
@@ -937,8 +935,7 @@ static void fill_comm_table(vt_ctx* ctx, PoissonData& P)
         tb.x[r] = reinterpret_cast<double*>(base + lay.x);
         tb.z[r] = reinterpret_cast<double*>(base + lay.z);
         tb.grad[r] = reinterpret_cast<double*>(base + lay.grad);
-        tb.red[r] = reinterpret_cast<double*>(base + lay.red);
-        tb.flagR[r] = reinterpret_cast<uint32_t*>(base + lay.flagR);
+        tb.ll[r] = reinterpret_cast<unsigned long long*>(base + lay.ll);
         tb.flagB[r] = reinterpret_cast<uint32_t*>(base + lay.flagB);
     }
     if (!P.commTable) VT_CUDA(cudaMalloc(&P.commTable, sizeof(CommTable)));
