@@ -136,7 +136,8 @@ def test_generic_entry_points_on_tucker_species(oracle_mod):
     ctx.close()
 
 
-@pytest.mark.parametrize("n,cap", [((32, 24, 20), 0), ((48, 40, 36), 8), ((20, 64, 18), 8)])
+@pytest.mark.parametrize("n,cap", [((32, 24, 20), 0), ((48, 40, 36), 8), ((20, 64, 18), 8),
+                                   ((32, 32, 32), 8), ((33, 25, 17), 8), ((24, 36, 18), 16), ((48, 48, 40), 12)])
 def test_large_grids_against_dense_statement(n, cap):
     """Velocity grids above 16 nodes per axis take the 256-thread kernel (tiled Gram matrices with
     and without register prefetch, C5 shape 48^3 at rank 8).  The oracle's Tucker algebra is too
@@ -331,3 +332,66 @@ np.save(sys.argv[1], ctx.tucker_get_pdf(g, f.shape[1]))
             assert r.returncode == 0, r.stderr[-2000:]
             outs.append(np.load(path))
     assert rel_l2(outs[0], outs[1]) <= 1e-9
+
+
+@pytest.mark.parametrize("n,cap", [((34, 20, 18), 8), ((40, 33, 26), 16)])
+def test_slab_kernel_agrees_with_general_kernel(n, cap):
+    """csrc/tucker_slab.cu (slab-streaming, tensor-core contractions, parallel Jacobi) serves grids of
+    33..48 nodes per axis with rank caps <= 16 and eps >= 5.5e-7; VT_TUCKER_KERNEL=general keeps k_tucker.
+    Both evaluate the same six truncated HOSVDs: same ranks, state and moments within the compression
+    error, on a mesh with Absorbing (collecting), Free and Source faces next to the periodic ones."""
+    import os
+    import vlasovtucker_b200 as vtb
+    from vlasovtucker_b200 import synthetic
+    mt = synthetic.periodic_kuhn_tables(2, 2, 1, (1.0, 1.0, 0.5), brick=(1, 1, 1))
+    vmin, vmax = [-3.0, -2.5, -2.0], [3.0, 2.5, 2.0]
+    eps, dt = 1e-6, 2e-3
+    _, V = vgrid(n, vmin, vmax)
+    rng = np.random.default_rng(11)
+    f = np.zeros((mt.nTets, n[0] * n[1] * n[2]))
+    for t in range(mt.nTets):
+        for _ in range(3):
+            c, s = rng.uniform(-0.8, 0.8, 3), rng.uniform(0.5, 1.0, 3)
+            f[t] += rng.uniform(0.5, 1.5) * np.exp(-0.5 * sum(((V[k] - c[k]) / s[k]) ** 2 for k in range(3)))
+    src = np.exp(-0.5 * sum((V[k] / 0.8) ** 2 for k in range(3)))[None, :]
+    E = rng.standard_normal((mt.nTets, 3))
+    bc = np.full((mt.nTets, 4), vtb.PBC["Periodic"], np.uint8)
+    collect = np.zeros((mt.nTets, 4), np.uint8)
+    source = np.full((mt.nTets, 4), -1, np.int32)
+    kinds = [vtb.PBC["Absorbing"], vtb.PBC["Free"], vtb.PBC["Source"], vtb.PBC["Absorbing"]]
+    ent = np.asarray(mt.entity).reshape(mt.nTets, 4)
+    for i, (t, j) in enumerate(zip(*np.nonzero(ent > 0))):   # every second face on the box surface gets a wall BC
+        if i % 2:
+            continue
+        bc[t, j] = kinds[(i // 2) % 4]
+        if bc[t, j] == vtb.PBC["Absorbing"]:
+            collect[t, j] = 1
+        if bc[t, j] == vtb.PBC["Source"]:
+            source[t, j] = 0
+    out = {}
+    for kernel in ("general", "slab"):
+        os.environ["VT_TUCKER_KERNEL"] = kernel
+        try:
+            ctx = vtb.Context(0)
+            ctx.mesh_upload(mt)
+            g = ctx.species_create(n, vmin, vmax, 1.0, -1.0)
+            ctx.set_source_pdfs(g, src)
+            ctx.set_face_bc(g, bc, collect, source)
+            ctx.tucker_enable(g, eps, cap)
+            ctx.tucker_set_pdf(g, f)
+            ctx.field_set(E)
+            for _ in range(2):
+                ctx.step_tucker(g, dt)
+            ents = sorted(set(int(e) for e in np.asarray(mt.entity).ravel() if e > 0))
+            out[kernel] = (ctx.tucker_get_pdf(g, f.shape[1]), ctx.tucker_ranks(g).copy(), ctx.tucker_density(g).copy(),
+                           np.array([ctx.wall_charge(g, e) for e in ents]))
+            ctx.close()
+        finally:
+            os.environ.pop("VT_TUCKER_KERNEL", None)
+    fa, ra, da, wa = out["general"]
+    fb, rb, db, wb = out["slab"]
+    assert rel_l2(fb, fa) <= 2 * eps
+    assert np.abs(ra - rb).max() <= 1
+    assert rel_l2(db, da) <= 2 * eps
+    assert np.allclose(wb, wa, rtol=1e-5, atol=1e-12 * max(1.0, np.abs(wa).max()))
+    assert np.abs(wa).max() > 0

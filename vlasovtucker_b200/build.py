@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build", "obj")
 LIB = os.path.join(LIBDIR, "libvt_b200.so")
-SOURCES = ["vt_api.cu", "full_step.cu", "full_step_tma.cu", "poisson.cu", "halo.cu", "tucker.cu", "group.cu"]
+SOURCES = ["vt_api.cu", "full_step.cu", "full_step_tma.cu", "poisson.cu", "halo.cu", "tucker.cu", "tucker_slab.cu", "group.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 # the system host compiler; the image exports CXX/CC pointing at a wrapper nvcc cannot use

@@ -22,41 +22,18 @@
 // Accuracy note: singular values come from Gram matrices, so values below ~1e-8 sigma_1 are noise;
 // the rank rule is exact for compression errors >= ~1e-7 (the examples use 1e-6).  For the class
 // default 1e-10 the result is still a valid Tucker approximation within ~1e-8.
-#include "vt_internal.h"
+#include "tucker_internal.h"
 
 #include <algorithm>
 #include <cstring>
 
 namespace vt {
 
-struct TuckerState {
-    int rcap[3];                 // stored rank capacity per mode = min(maxRank, n)
-    size_t coreCap, slot;        // doubles per tet: core, whole slot (core + 3 factors)
-    void* block = nullptr;       // one allocation (one CUDA-IPC handle): buf[0] | buf[1] | ranks[0] | ranks[1]
-    size_t rows = 0;             // owned + ghost rows
-    double* buf[2] = {nullptr, nullptr};   // compressed state, ping-pong
-    int* ranks[2] = {nullptr, nullptr};    // 3 per tet
-    // multi-GPU: the peers' blocks, for the ghost copies of boundary tets
-    double* peerBuf[kMaxPeers][2] = {};
-    int* peerRanks[kMaxPeers][2] = {};
-    int nPeers = 0;
-    double* vnabs = nullptr;     // |v.n| per face as rank-<=6 Tucker tensors (solver.cpp:282): 4 slots per owned tet
-    int* vnabsRanks = nullptr;   // 3 per (tet, face)
-    size_t vslot = 0;            // doubles per slot: 6^3 core + 6 (n0 + n1 + n2)
-    double* scratch = nullptr;   // per-CTA dense work space
-    int scratchCTAs = 0;
-    double comprErr = 1e-10;
-    int maxRank = 0;
-    int cur = 0;
-    bool vnabsValid = false;
-    bool denseValid = false;     // sp.f[sp.cur] holds the reconstruction of buf[cur]
-};
 
 namespace {
 
 constexpr int kThreads = 256;        // CTA size for velocity grids above 16 nodes per axis
 constexpr int kThreadsSmall = 128;   // ... and up to 16: more tets in flight per SM hide the eigen-solver's latency
-constexpr int kMaxN = 64;
 
 struct Dims {
     int n[3];
@@ -911,39 +888,6 @@ __device__ void reconstruct(const double* core, const int r[3], double* const U[
     if (prof) prof[4] += clock64() - t0;
 }
 
-struct TuckerParams {
-    int nOwned;
-    int n[3], N;
-    int rcap[3];
-    size_t coreCap, slot;
-    const double* in;      // compressed state at step n
-    const int* rin;
-    double* out;           // compressed state at step n+1
-    int* rout;
-    const TetRec* rec;
-    const double* E;
-    double* vnabs;         // [nOwned][4][vslot]: core 6^3, then U0 (n0 x 6), U1, U2
-    int* vnabsRanks;       // [nOwned][4][3]
-    size_t vslot;
-    const double* src;     // dense source PDFs (Source BC), rows of N
-    double* density;
-    double* wall;
-    double* scratch;       // per CTA: 5 N + 3 kMaxN*kMaxN(U work) doubles
-    size_t scratchPerCTA;
-    double vmin[3], step[3], inv2h[3];
-    double qm, ext[3], dt, wallScale, cellVolume;
-    double eps;
-    int maxRank;
-    const double* denseIn;   // set_pdf path: dense rows to compress (mode 1)
-    double* denseOut;        // get_pdf path: dense rows reconstructed (mode 2)
-    int first;
-    int mode;                // 0 step, 1 compress dense input, 2 reconstruct, 3 |v.n| tables
-    double epsAbs;           // mode 3: compression error for |v.n| (rank cap 6)
-    long long* prof;         // optional: 8 phase timers in clock cycles (VT_TUCKER_PROFILE)
-    int gramDmma;            // 1: Gram matrices by mma.sync f64 (the default), 0: DFMA (VT_TUCKER_GRAM=dfma)
-    double* peerOut[kMaxPeers];   // multi-GPU: peers' state buffers receiving the ghost copies
-    int* peerRout[kMaxPeers];
-};
 
 __device__ void slot_ptrs(double* base, const TuckerParams& P, double*& core, double* U[3])
 {
@@ -1583,8 +1527,8 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
         static const bool profile = getenv("VT_TUCKER_PROFILE") != nullptr;
         long long* profDev = nullptr;
         if (profile) {
-            VT_CUDA(cudaMalloc(&profDev, 8 * sizeof(long long)));
-            VT_CUDA(cudaMemsetAsync(profDev, 0, 8 * sizeof(long long), ctx->stream));
+            VT_CUDA(cudaMalloc(&profDev, 24 * sizeof(long long)));
+            VT_CUDA(cudaMemsetAsync(profDev, 0, 24 * sizeof(long long), ctx->stream));
             P.prof = profDev;
         }
         cudaEvent_t e0 = ctx->ev0, e1 = ctx->ev1;
@@ -1600,17 +1544,26 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
             e1 = ctx->kernelEvents[ctx->kernelEventsUsed++];
         }
         VT_CUDA(cudaEventRecord(e0, ctx->stream));
-        launch(ctx, ts, P);
+        const bool slab = slab_eligible(ctx, P);   // tucker_slab.cu: slab-streaming kernel where it applies
+        if (slab) launch_tucker_slab(ctx, ts, P);
+        else launch(ctx, ts, P);
         VT_CUDA(cudaEventRecord(e1, ctx->stream));
         if (profile) {
-            long long h[8];
+            long long h[24];
             VT_CUDA(cudaStreamSynchronize(ctx->stream));
             VT_CUDA(cudaMemcpy(h, profDev, sizeof(h), cudaMemcpyDeviceToHost));
             cudaFree(profDev);
-            fprintf(stderr,
-                    "[vt_step_tucker] cycles of CTA 0: gram %lld  eig %lld  select %lld  project %lld  reconstruct %lld  "
-                    "flux %lld  derivative %lld  total %lld\n",
-                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+            if (slab)
+                fprintf(stderr,
+                        "[vt_step_tucker, slab kernel] cycles of CTA 0: pass 1 (expand + X + G0, G1) %lld  pass 2 (G2) %lld  "
+                        "Cholesky + L^T L %lld  Jacobi %lld  select %lld  pass 3 (core) %lld  total %lld | pass 1 phases: M2 %lld  T %lld  "
+                        "expand %lld  X %lld  Gram %lld | Jacobi rounds %lld sweeps %lld: scan %lld  phase 1 %lld  phase 2 %lld | active sets of the last problem, by sweep (modes 0|1|2): %llx %llx %llx %llx %llx %llx\n",
+                        h[0], h[1], h[5], h[2], h[3], h[4], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17], h[18], h[19], h[20], h[21], h[22], h[23]);
+            else
+                fprintf(stderr,
+                        "[vt_step_tucker] cycles of CTA 0: gram %lld  eig %lld  select %lld  project %lld  reconstruct %lld  "
+                        "flux %lld  derivative %lld  total %lld\n",
+                        h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
         }
         ts.cur ^= 1;
         ts.denseValid = false;
