@@ -302,6 +302,27 @@ def tucker_flops_executed(n):
     return float(6 * (gram + proj) + 9 * 3 * 2 * n ** 4)
 
 
+def tucker_flops_slab(n, r):
+    """Flops the slab-streaming kernel (csrc/tucker_slab.cu) executes per tet-step on an n^3 grid at rank r, all faces
+    paired: its tensor-core contractions counted DMMA by DMMA (512 flops each) — slab expansions, Gram matrices
+    (upper triangle of 8x8 blocks), projections — plus ~20 flops per node and rounding for the flux / update arithmetic.
+    The eigen-solves (pivoted Cholesky + Jacobi on ~15 x 15 matrices) are latency, not flops, and are left out."""
+    p = (n + 7) // 8 * 8
+    nb = p // 8
+    pairs = nb * (nb + 1) // 2
+    k4 = lambda x: (x + 3) // 4
+    b8 = lambda x: (x + 7) // 8
+    dmma = 0
+    for ops in (3, 3, 3, 3, 1, 1):                       # four faces (neighbour, |v.n|, previous rhs / own f), acceleration, Euler update
+        ranks = [r, 6, r][:ops] if ops == 3 else [r]
+        expand = sum(nb * b8(q) * k4(q) + nb * nb * k4(q) for q in ranks)     # T = U0 M2, slab = T U1^T
+        gram01 = 2 * pairs * (p // 4)
+        gram2 = pairs * (p // 4)
+        proj = b8(r) * nb * (p // 4) + b8(r) * b8(r) * (p // 4)
+        dmma += n * (expand + gram01 + proj) + n * gram2
+    return float(512 * dmma + 6 * 20 * n ** 3)
+
+
 def tucker_cpu_baseline(nv, rank, eps, hexes=(1, 1, 1), budget_s=20.0):
     """The oracle's Tucker algebra (oracle/oracle_tucker.cpp: operator+, Hadamard product, QR + HOSVD
     rounding as src/tucker.cpp) on a small Kuhn box with the C5 inputs, all host cores."""
@@ -423,6 +444,7 @@ def run_tucker(args, rank_world_local, dist, torch, hexes, nv, rank_t, eps, step
         t_ms = float(t.item())
     ms_per_step = t_ms / steps
     ranks = ctx.tucker_ranks(sp)
+    which = ctx.tucker_last_kernel(sp)
     # end to end: E from host memory in, Density() out to host memory, every step
     if runner is not None:
         e2e_ms = runner.e2e(dt, max(1, steps // 2), barrier) / max(1, steps // 2)
@@ -451,7 +473,7 @@ def run_tucker(args, rank_world_local, dist, torch, hexes, nv, rank_t, eps, step
         return None
     kern_avg = kern_ms / max(1, kern_n)
     fl_ref = tucker_flops_survey(nv, rank_t, rank_t) * nT
-    fl_exe = tucker_flops_executed(nv) * nT
+    fl_exe = (tucker_flops_slab(nv, rank_t) if which == "slab" else tucker_flops_executed(nv)) * nT
     out = {
         "metric": "cell x v-node updates/s per step (Tucker format)", "value": nT * N * world / (ms_per_step * 1e-3),
         "unit": "updates/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
@@ -463,11 +485,14 @@ def run_tucker(args, rank_world_local, dist, torch, hexes, nv, rank_t, eps, step
                    "tet_updates_per_s": nT * world / (ms_per_step * 1e-3)},
         "roofline": {"bound": "fp64", "achieved": fl_ref / (kern_avg * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                      "frac": fl_ref / (kern_avg * 1e-3) / 1e12 / peak, "traffic": None,
-                     "peak_source": "DFMA probe in this run (vt_measure_dfma_peak)", "kernel": "k_tucker", "kernel_ms": kern_avg,
+                     "peak_source": "DFMA probe in this run (vt_measure_dfma_peak)",
+                     "kernel": "k_tucker_slab" if which == "slab" else "k_tucker", "kernel_ms": kern_avg,
                      "flops_per_tet_step_counted": fl_ref / nT,
                      "counted": "SURVEY.md §8d formula for the reference's six Compress calls (QR + core transform + 3 SVDs + projection)",
                      "executed_flops_per_tet_step": fl_exe / nT, "executed_tflops": fl_exe / (kern_avg * 1e-3) / 1e12,
-                     "executed": "dense formulation of csrc/tucker.cu: 6 x (3 Gram matrices + 3 projections) + reconstructions",
+                     "executed": ("slab-streaming kernel csrc/tucker_slab.cu: its DMMA contractions counted one by one (slab expansions, "
+                                  "upper-triangle Gram blocks, projections) + ~20 flops per node and rounding" if which == "slab" else
+                                  "dense formulation of csrc/tucker.cu: 6 x (3 Gram matrices + 3 projections) + reconstructions"),
                      "kernel_share_of_step": kern_ms / region_ms},
         "e2e": {"value": nT * N * world / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": 3 * nT * 8 * world,
                 "d2h_bytes_per_step": nT * 8 * world, "ms_per_step": e2e_ms,

@@ -17,6 +17,9 @@ KEYS = [
     "smsp__cycles_active.avg", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
     "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_global_ld.sum",
     "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "sm__ops_path_tensor_src_fp64.sum", "sm__ops_path_tensor_src_fp64.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed.avg.per_cycle_elapsed",
 ]
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "vt_tucker_get_ranks": (C.c_int, [C.c_void_p, C.c_int, c_ip]),
     "vt_tucker_get_factors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_ip, c_dp, c_dp, c_dp, c_dp]),
     "vt_tucker_density": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "vt_tucker_last_kernel": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "vt_step_tucker": (C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp]),
     "vt_tucker_halo_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vt_tucker_halo_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

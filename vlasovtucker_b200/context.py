@@ -347,6 +347,12 @@ class Context:
         capi.check(self.lib.vt_tucker_density(self.h, sp, capi.dp(d)))
         return d
 
+    def tucker_last_kernel(self, sp):
+        """'general' (csrc/tucker.cu) or 'slab' (csrc/tucker_slab.cu): the kernel the last step_tucker ran."""
+        k = C.c_int()
+        capi.check(self.lib.vt_tucker_last_kernel(self.h, sp, C.byref(k)))
+        return {0: None, 1: "general", 2: "slab"}[k.value]
+
     TUCKER_HALO_HANDLE_BYTES = 128
 
     def tucker_halo_export(self, sp):

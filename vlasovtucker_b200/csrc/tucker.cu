@@ -1496,6 +1496,18 @@ int vt_tucker_density(vt_ctx* ctx, int species, double* density)
     });
 }
 
+int vt_tucker_last_kernel(vt_ctx* ctx, int species, int* kernel)
+{
+    if (ctx->group) {
+        vt_set_error("vt_tucker_last_kernel: not available on a device group");
+        return 1;
+    }
+    return guard([&] {
+        Species& sp = species_of(ctx, species);
+        *kernel = state_of(sp).lastKernel;
+    });
+}
+
 int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
 {
     if (ctx->group) return vt::group_step(ctx, species, dt, ext, true);
@@ -1547,6 +1559,7 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
         const bool slab = slab_eligible(ctx, P);   // tucker_slab.cu: slab-streaming kernel where it applies
         if (slab) launch_tucker_slab(ctx, ts, P);
         else launch(ctx, ts, P);
+        ts.lastKernel = slab ? 2 : 1;
         VT_CUDA(cudaEventRecord(e1, ctx->stream));
         if (profile) {
             long long h[24];

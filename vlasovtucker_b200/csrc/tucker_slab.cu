@@ -182,6 +182,7 @@ struct JacobiWork {
     int* na;             // [3] their number (made even with an idle index)
     unsigned* mask;      // [3][2] the same set as bits
     double* crit;        // [3][3] see needs_rotation
+    double* invTr;       // [3] 1 / trace
     long long* prof;
 };
 
@@ -200,6 +201,25 @@ __device__ __forceinline__ bool needs_rotation(double gpq, double gpp, double gq
 {
     const double a2 = gpq * gpq, gp = fabs(gpp), gq = fabs(gqq);
     return fabs(gpq) > crit[0] && a2 > crit[1] * fmax(gp, gq) && gp + gq > crit[2] && a2 > 1e-32 * gp * gq;
+}
+
+// The rotation (c, s) for the pair with off-diagonal gpq and diagonal difference d = gqq - gpp.  The tangent is
+// computed in single precision (no double-precision division or square root on the critical path of a round):
+// an inexact angle only means that g_pq is not annihilated completely, which the next sweep sees.  What has to
+// be exact is c^2 + s^2 = 1 — the transformation must stay orthogonal — so the pair is renormalised in double
+// precision with the series of 1 / sqrt(1 + delta).  invTr scales the entries into single-precision range.
+__device__ __forceinline__ void rotation_of(double gpq, double d, double invTr, double& c, double& sn)
+{
+    const float af = (float)(2.0 * gpq * invTr), df = (float)(d * invTr);
+    const float den = fabsf(df) + sqrtf(fmaf(df, df, af * af));
+    float tf = den > 0.0f ? af / den : 0.0f;
+    if (df < 0.0f) tf = -tf;
+    const float cf = rsqrtf(fmaf(tf, tf, 1.0f));
+    double cc = (double)cf, ss = (double)(tf * cf);
+    const double delta = fma(cc, cc, fma(ss, ss, -1.0));
+    const double corr = fma(delta, fma(delta, 0.375, -0.5), 1.0);
+    c = cc * corr;
+    sn = ss * corr;
 }
 
 // Parallel two-sided Jacobi on three symmetric matrices at once (scripts/prototypes/jacobi_round_robin.py
@@ -301,20 +321,14 @@ __device__ void jacobi3(const JacobiWork& wShared)
                     const int ld = w.ld[k];
                     const double* G = w.G[k];
                     const double gpq = G[p + ld * q], gpp = G[p + ld * p], gqq = G[q + ld * q];
-                    double c = 1.0, sn = 0.0, t = 0.0;
+                    double c = 1.0, sn = 0.0;
                     int rotated = 0;
                     if (needs_rotation(gpq, gpp, gqq, w.crit + 3 * k)) {
-                        // t = tan of the rotation angle: the smaller root of t^2 + 2 tau t - 1 = 0, tau = (gqq - gpp) / (2 gpq)
-                        const double d = gqq - gpp;
-                        const double den = fabs(d) + sqrt(fma(d, d, 4.0 * gpq * gpq));
-                        t = (d >= 0.0 ? 2.0 * gpq : -2.0 * gpq) / den;
-                        c = rsqrt(fma(t, t, 1.0));
-                        sn = t * c;
+                        rotation_of(gpq, gqq - gpp, w.invTr[k], c, sn);
                         rotated = 1;
                     }
                     w.rotC[kMaxSlots * k + lane] = c;
                     w.rotS[kMaxSlots * k + lane] = sn;
-                    w.rotT[kMaxSlots * k + lane] = t;
                     w.rotPQ[kMaxSlots * k + lane] = p | (q << 8) | (rotated << 16);
                 }
             }
@@ -369,11 +383,11 @@ __device__ void jacobi3(const JacobiWork& wShared)
                         const double nQR = cj[k] * m[k][2] - sj[k] * m[k][3], nQS = sj[k] * m[k][2] + cj[k] * m[k][3];
                         const double oPR = ci[k] * nPR - si[k] * nQR, oQR = si[k] * nPR + ci[k] * nQR;
                         const double oPS = ci[k] * nPS - si[k] * nQS, oQS = si[k] * nPS + ci[k] * nQS;
-                        if (i == j) {   // rows and columns are the same pair: P = R, Q = S
+                        if (i == j) {   // rows and columns are the same pair: P = R, Q = S; what is left of g_PQ is kept
                             G[P[k] + ld * P[k]] = oPR;
                             G[Q[k] + ld * Q[k]] = oQS;
-                            G[P[k] + ld * Q[k]] = 0.0;
-                            G[Q[k] + ld * P[k]] = 0.0;
+                            G[P[k] + ld * Q[k]] = oPS;
+                            G[Q[k] + ld * P[k]] = oPS;
                         } else {
                             G[P[k] + ld * R[k]] = oPR;
                             G[R[k] + ld * P[k]] = oPR;
@@ -441,6 +455,137 @@ __device__ void jacobi3(const JacobiWork& wShared)
     }
 }
 
+// The same method for ONE matrix on ONE warp (no block barrier): after the Cholesky reduction the problems are
+// small (12-20 rows for smooth tensors), a round then is a handful of rotations and the three matrices run side
+// by side on three warps.  Used when every reduced matrix has at most 24 rows; larger ones take jacobi3.
+__device__ void jacobi_warp(const JacobiWork& ws, int k)
+{
+    const int lane = threadIdx.x & 31;
+    const int n = ws.n[k], ld = ws.ld[k], pk = ws.p[k];
+    double* const G = ws.G[k];
+    double* const V = ws.V[k];
+    int* const act = ws.act + 64 * k;
+    double* const rotC = ws.rotC + kMaxSlots * k;
+    double* const rotS = ws.rotS + kMaxSlots * k;
+    int* const rotPQ = ws.rotPQ + kMaxSlots * k;
+    const double crit[3] = {ws.crit[3 * k], ws.crit[3 * k + 1], ws.crit[3 * k + 2]};
+    const double invTr = ws.invTr[k];
+    long long* const wprof = (lane == 0 && k == 0) ? ws.prof : nullptr;
+    for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
+        bool hit0 = false, hit1 = false;
+        if (lane < n) {
+            const double gii = G[lane + ld * lane];
+            for (int q = 0; q < n; q++)
+                if (q != lane) hit0 |= needs_rotation(G[lane + ld * q], gii, G[q + ld * q], crit);
+        }
+        if (lane + 32 < n) {
+            const int r = lane + 32;
+            const double gii = G[r + ld * r];
+            for (int q = 0; q < n; q++)
+                if (q != r) hit1 |= needs_rotation(G[r + ld * q], gii, G[q + ld * q], crit);
+        }
+        unsigned m0 = __ballot_sync(0xffffffffu, hit0), m1 = __ballot_sync(0xffffffffu, hit1);
+        int na = __popc(m0) + __popc(m1);
+        if (na == 0) break;
+        if (na & 1) {   // an idle index completes the last pair (it exists: the padded dimension is even)
+            int d = 0;
+            while (d < pk && ((d < 32 ? m0 >> d : m1 >> (d - 32)) & 1u)) d++;
+            if (d < 32) m0 |= 1u << d;
+            else m1 |= 1u << (d - 32);
+            na++;
+        }
+        const unsigned below = (1u << lane) - 1u;
+        if ((m0 >> lane) & 1u) act[__popc(m0 & below)] = lane;
+        if ((m1 >> lane) & 1u) act[__popc(m0) + __popc(m1 & below)] = 32 + lane;
+        __syncwarp();
+        const int h = na >> 1;
+        if (wprof) {
+            wprof[13] += na - 1;
+            wprof[14] += 1;
+        }
+        for (int s = 0; s < na - 1; s++) {
+            if (lane < h) {
+                int a, b;
+                if (lane == 0) {
+                    a = na - 1;
+                    b = s;
+                } else {
+                    a = s + lane;
+                    if (a >= na - 1) a -= na - 1;
+                    b = s - lane;
+                    if (b < 0) b += na - 1;
+                }
+                int p = act[a], q = act[b];
+                if (p > q) {
+                    const int xx = p;
+                    p = q;
+                    q = xx;
+                }
+                const double gpq = G[p + ld * q], gpp = G[p + ld * p], gqq = G[q + ld * q];
+                double c = 1.0, sn = 0.0;
+                int rotated = 0;
+                if (needs_rotation(gpq, gpp, gqq, crit)) {
+                    rotation_of(gpq, gqq - gpp, invTr, c, sn);
+                    rotated = 1;
+                }
+                rotC[lane] = c;
+                rotS[lane] = sn;
+                rotPQ[lane] = p | (q << 8) | (rotated << 16);
+            }
+            __syncwarp();
+            // 2x2 blocks of G over the pairs i <= j
+            for (int e = lane; e < h * h; e += 32) {
+                const int i = e % h, j = e / h;
+                if (i > j) continue;
+                const int pqi = rotPQ[i], pqj = rotPQ[j];
+                if (((pqi | pqj) >> 16) == 0) continue;
+                const int P = pqi & 255, Q = (pqi >> 8) & 255, R = pqj & 255, S = (pqj >> 8) & 255;
+                const double ci = rotC[i], si = rotS[i], cj = rotC[j], sj = rotS[j];
+                const double mPR = G[P + ld * R], mPS = G[P + ld * S], mQR = G[Q + ld * R], mQS = G[Q + ld * S];
+                const double nPR = cj * mPR - sj * mPS, nPS = sj * mPR + cj * mPS;
+                const double nQR = cj * mQR - sj * mQS, nQS = sj * mQR + cj * mQS;
+                const double oPR = ci * nPR - si * nQR, oQR = si * nPR + ci * nQR;
+                const double oPS = ci * nPS - si * nQS, oQS = si * nPS + ci * nQS;
+                if (i == j) {   // what is left of g_PQ is kept: the similarity transformation stays exact
+                    G[P + ld * P] = oPR;
+                    G[Q + ld * Q] = oQS;
+                    G[P + ld * Q] = oPS;
+                    G[Q + ld * P] = oPS;
+                } else {
+                    G[P + ld * R] = oPR;
+                    G[R + ld * P] = oPR;
+                    G[P + ld * S] = oPS;
+                    G[S + ld * P] = oPS;
+                    G[Q + ld * R] = oQR;
+                    G[R + ld * Q] = oQR;
+                    G[Q + ld * S] = oQS;
+                    G[S + ld * Q] = oQS;
+                }
+            }
+            // rows: V <- V J, and G(x, .) of the idle indices x
+            for (int e = lane; e < n * h; e += 32) {
+                const int x = e % n, j = e / n;
+                const int pq = rotPQ[j];
+                if ((pq >> 16) == 0) continue;
+                const int P = pq & 255, Q = (pq >> 8) & 255;
+                const double c = rotC[j], sn = rotS[j];
+                const double vp = V[x + ld * P], vq = V[x + ld * Q];
+                V[x + ld * P] = c * vp - sn * vq;
+                V[x + ld * Q] = sn * vp + c * vq;
+                if (((x < 32 ? m0 >> x : m1 >> (x - 32)) & 1u) == 0) {
+                    const double gp = G[x + ld * P], gq = G[x + ld * Q];
+                    const double np = c * gp - sn * gq, nq = sn * gp + c * gq;
+                    G[x + ld * P] = np;
+                    G[P + ld * x] = np;
+                    G[x + ld * Q] = nq;
+                    G[Q + ld * x] = nq;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 enum { KIND_FACE = 0, KIND_ACCEL = 1, KIND_FINAL = 2 };
 
 // Everything the passes share, in SHARED memory.  With ~190 KB of shared memory in use the L1 cache is almost
@@ -471,7 +616,7 @@ struct SlabShared {
     int rotPQ[3 * kMaxSlots];
     int act[3 * 64], na[3];
     unsigned mask[6];
-    double crit[9];
+    double crit[9], invTr[3];
     double red[NW][5];
     double colSum[3][16];
     // Gram tasks of every warp, one packed word each: mode (pass 1) or half of the sum (pass 2) | I << 4 | J << 8; 15 = none
@@ -605,7 +750,7 @@ __device__ __noinline__ double pass1(SlabShared<NW, PPW>& S, double* sm)
         for (int s = 0; s < 3; s++) {
             if (!S.op[s].on) continue;
             const int r0 = S.op[s].r[0], r1 = S.op[s].r[1], r2 = S.op[s].r[2];
-            const int r0K = ceil4(r0), r1K = ceil4(r1);
+            const int r0K = ceil4(r0), r1K = ceil8(r1);
             const double* u2 = sm + L.oFac[s][2] + i2;
             const double* core = S.op[s].core;
             double* M2 = sm + L.oM2[s] + set * mSet;
@@ -631,18 +776,23 @@ __device__ __noinline__ double pass1(SlabShared<NW, PPW>& S, double* sm)
     for (int i2 = 0; i2 < n2; i2++) {
         long long tq = prof ? clock64() : 0;
         const int set = i2 & 1;
-        // ---- phase A: T = U0 M2 (p0 x r1K, columns beyond the rank are zero), M2 of the next slab, prefetches
-        for (int s = 0; s < 3; s++) {
-            if (!S.op[s].on) continue;
-            const int r0 = S.op[s].r[0], r1K = ceil4(S.op[s].r[1]);
-            const double* U0 = sm + L.oFac[s][0];
-            const double* M2 = sm + L.oM2[s] + set * mSet;
-            double* Ts = sm + L.oT[s] + set * tSet;
-            for (int e = tid; e < p0 * r1K; e += T) {
-                const int i0 = e % p0, b = e / p0;
-                double v = 0.0;
-                for (int a = 0; a < r0; a++) v = fma(U0[i0 + LD * a], M2[a + rK * b], v);
-                Ts[i0 + LD * b] = v;
+        // ---- phase A: T = U0 M2 on the tensor cores (p0 x r1, the columns a phase-B step reads beyond the rank are
+        // zero because M2's are), M2 of the next slab, prefetches
+        {
+            int task = warp;
+            for (int s = 0; s < 3; s++) {
+                if (!S.op[s].on) continue;
+                const int K4 = ceil4(S.op[s].r[0]) / 4, nJ = ceil8(S.op[s].r[1]) / 8;
+                const double* U0 = sm + L.oFac[s][0];
+                const double* M2 = sm + L.oM2[s] + set * mSet;
+                double* Ts = sm + L.oT[s] + set * tSet;
+                for (; task < nb0 * nJ; task += NW) {
+                    const int I = task % nb0, J = task / nb0;
+                    double acc[2] = {0.0, 0.0};
+                    warp_mma(acc, U0 + 8 * I, 1, LD, M2 + rK * 8 * J, 1, rK, K4);
+                    warp_store(acc, Ts + 8 * I + LD * 8 * J, 1, LD);
+                }
+                task -= nb0 * nJ;
             }
         }
         if (i2 + 1 < n2) make_M2(i2 + 1, set ^ 1);
@@ -835,7 +985,7 @@ __device__ __noinline__ void gram_pass2(SlabShared<NW, PPW>& S, double* sm)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const SlabLay& L = S.L;
     const int n0 = S.P.n[0], n1 = S.P.n[1], n2 = S.P.n[2], M = n0 * n1;
-    const int p0 = L.p[0], p1 = L.p[1], LD = L.LD;
+    const int p0 = L.p[0], LD = L.LD;
     const bool vec2 = (n0 % 2) == 0;
     double* const ring0 = sm + L.oV[0];
     const int slabSz = L.slab;
@@ -979,6 +1129,7 @@ __device__ __noinline__ void eigen_and_select(SlabShared<NW, PPW>& S, double* sm
             S.crit[3 * k] = fmax(1e-16, 0.02 * eps * eps) * tr;
             S.crit[3 * k + 1] = 1e-6 * eps * eps * tr;
             S.crit[3 * k + 2] = 0.03 * eps * eps * tr;
+            S.invTr[k] = tr > 0.0 ? 1.0 / tr : 0.0;
         }
     }
     __syncthreads();
@@ -1008,7 +1159,12 @@ __device__ __noinline__ void eigen_and_select(SlabShared<NW, PPW>& S, double* sm
         S.prof[5] += now - tp;
         tp = now;
     }
-    jacobi3<T>(S.jw);
+    if (max(S.kdim[0], max(S.kdim[1], S.kdim[2])) <= 24) {
+        if (warp < 3) jacobi_warp(S.jw, warp);
+        __syncthreads();
+    } else {
+        jacobi3<T>(S.jw);
+    }
     if (prof) {
         const long long now = clock64();
         S.prof[2] += now - tp;
@@ -1280,6 +1436,7 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) k_tucker_slab(const Tucke
         jw.na = S.na;
         jw.mask = S.mask;
         jw.crit = S.crit;
+        jw.invTr = S.invTr;
         S.profOn = (S.P.prof && blockIdx.x == 0) ? 1 : 0;
         jw.prof = S.profOn ? S.prof : nullptr;
         double* scr = S.P.scratch + (size_t)blockIdx.x * S.P.scratchPerCTA;

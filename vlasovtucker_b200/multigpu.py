@@ -232,43 +232,6 @@ class PartitionedPoisson:
         dist.barrier()
 
 
-class ReplicatedField:
-    """Field solve for a partitioned run.  The Poisson unknowns are one double per tet — 1/N_v of
-    the kinetic state — so every rank solves the *global* system redundantly with the same
-    deterministic kernels (second context holding the global mesh) and keeps E for its own rows:
-    the result is bit-identical on all ranks and to the single-GPU loop.  Per step each rank
-    contributes the charge density of its owned tets (solver.cpp:98-105); that all-gather is the
-    only collective of the coupled loop."""
-
-    def __init__(self, local_device, global_tables, lp, dist, bc_type, bc_value=None, bc_normal_grad=None):
-        self.lp, self.dist = lp, dist
-        self.nT = global_tables.nTets
-        self.g = Context(local_device)
-        self.g.mesh_upload(global_tables)
-        self.g.poisson_setup(bc_type, bc_value, bc_normal_grad)
-        ids = [None] * dist.get_world_size()
-        dist.all_gather_object(ids, np.asarray(lp.owned, np.int64))
-        self.owned_of = ids
-
-    def solve(self, ctx, species, charges, background=None):
-        """rho = sum_s charge_s * Density_s + background on the global mesh, Poisson solve, E of the
-        owned rows into ``ctx``.  Returns (rho, phi, E) of the global mesh."""
-        local = np.zeros(len(self.lp.owned))
-        for sp, q in zip(species, charges):
-            local += q * ctx.density(sp)
-        parts = [None] * self.dist.get_world_size()
-        self.dist.all_gather_object(parts, local)
-        rho = np.zeros(self.nT) if background is None else np.array(background, dtype=np.float64)
-        for ids, p in zip(self.owned_of, parts):
-            rho[ids] += p
-        phi, E = self.g.poisson_solve(rho)
-        ctx.field_set(E[self.lp.owned])
-        return rho, phi, E
-
-    def close(self):
-        self.g.close()
-
-
 def wall_charge_total(ctx, sp, entity, dist):
     """Absorbed charge of one boundary entity summed over the ranks (solver.cpp:171-178 accumulates
     it per face; the faces of an entity are spread over the partitions)."""
