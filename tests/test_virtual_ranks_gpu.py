@@ -119,13 +119,14 @@ def test_virtual_ranks_walls_unstructured(vt, oracle_mod):
     assert qref != 0 and abs(q - qref) <= 1e-12 * abs(qref)
 
 
-def test_virtual_ranks_tucker_bit_identical(vt):
-    """Tucker species: the step kernel mirrors every boundary tet's new core, factors and ranks into
-    the peers' ghost slots."""
+@pytest.mark.parametrize("n,cap,kernel", [((12, 10, 8), 0, "general"), ((34, 12, 10), 8, "slab")])
+def test_virtual_ranks_tucker_bit_identical(vt, n, cap, kernel):
+    """Tucker species: the step kernel (the general one, and the slab-streaming one for grids above 32 nodes
+    per axis) mirrors every boundary tet's new core, factors and ranks into the peers' ghost slots."""
     from vlasovtucker_b200 import multigpu, partition as part, synthetic
     dims = (4, 2, 2)
     mt = synthetic.periodic_kuhn_tables(*dims, (2.0, 1.0, 1.0))
-    n, vmin, vmax = (12, 10, 8), [-3.0, -2.0, -2.0], [3.0, 2.0, 2.0]
+    vmin, vmax = [-3.0, -2.0, -2.0], [3.0, 2.0, 2.0]
     ax = [np.linspace(vmin[k], vmax[k], n[k]) for k in range(3)]
     V0, V1, V2 = np.meshgrid(*ax, indexing="ij")
     x = mt.tetCentroid[:, 0]
@@ -135,7 +136,7 @@ def test_virtual_ranks_tucker_bit_identical(vt):
     world, steps, dt, eps = 2, 3, 2e-3, 1e-6
     owner = part.rcb_owner(mt.tetCentroid, world)
     vr = multigpu.VirtualRanks(mt, owner, world)
-    ids = vr.species_create(n, vmin, vmax, 1.0, 1.5, tucker=(eps, 0))
+    ids = vr.species_create(n, vmin, vmax, 1.0, 1.5, tucker=(eps, cap))
     for r, ctx in enumerate(vr.ctxs):
         ctx.tucker_set_pdf(ids[r], f0[vr.lps[r].owned])
         ctx.field_set(E[vr.lps[r].owned])
@@ -143,6 +144,7 @@ def test_virtual_ranks_tucker_bit_identical(vt):
     for _ in range(steps):
         vr.step_tucker(ids, dt)
     vr.sync()
+    assert all(ctx.tucker_last_kernel(ids[r]) == kernel for r, ctx in enumerate(vr.ctxs))
     full = vr.gather([ctx.tucker_get_pdf(ids[r], n[0] * n[1] * n[2]) for r, ctx in enumerate(vr.ctxs)])
     ranks = vr.gather([ctx.tucker_ranks(ids[r]) for r, ctx in enumerate(vr.ctxs)])
     vr.close()
@@ -150,7 +152,7 @@ def test_virtual_ranks_tucker_bit_identical(vt):
     ctx.mesh_upload(mt)
     g = ctx.species_create(n, vmin, vmax, 1.0, 1.5)
     ctx.set_face_bc(g, np.full((mt.nTets, 4), vt.PBC["Periodic"], np.uint8))
-    ctx.tucker_enable(g, eps, 0)
+    ctx.tucker_enable(g, eps, cap)
     ctx.tucker_set_pdf(g, f0)
     ctx.field_set(E)
     for _ in range(steps):

@@ -1105,22 +1105,22 @@ __device__ __noinline__ void eigen_and_select(SlabShared<NW, PPW>& S, double* sm
             double c0 = (i0 < n && d0 >= 0.0) ? G[i0 + ld * bi] : 0.0, c1 = (i1 < n && d1 >= 0.0) ? G[i1 + ld * bi] : 0.0;
             for (int q = 0; q < j; q++) {
                 const double lp = Lm[bi + ld * q];
-                c0 = fma(-Lm[i0 + ld * q], lp, c0);
+                if (i0 < n) c0 = fma(-Lm[i0 + ld * q], lp, c0);
                 if (i1 < n) c1 = fma(-Lm[i1 + ld * q], lp, c1);
             }
             if (i0 == bi) c0 = best;
             if (i1 == bi) c1 = best;
             const double l0 = (i0 < n && d0 >= 0.0) ? c0 * inv : 0.0, l1 = (i1 < n && d1 >= 0.0) ? c1 * inv : 0.0;
-            Lm[i0 + ld * j] = l0;     // i0 < 32 <= ld: always inside the matrix
-            if (i1 < ld) Lm[i1 + ld * j] = l1;
+            if (i0 < n) Lm[i0 + ld * j] = l0;   // rows >= n are never read (the leading dimension may be below 32)
+            if (i1 < n) Lm[i1 + ld * j] = l1;
             if (d0 >= 0.0) d0 = i0 == bi ? -1.0 : fmax(d0 - l0 * l0, 0.0);
             if (d1 >= 0.0) d1 = i1 == bi ? -1.0 : fmax(d1 - l1 * l1, 0.0);
             kd = j + 1;
             __syncwarp();
         }
         if (kd == 0) {   // the zero tensor: one arbitrary direction, as an SVD would return
-            Lm[i0] = i0 == 0 ? 1.0 : 0.0;
-            if (i1 < ld) Lm[i1] = 0.0;
+            if (i0 < n) Lm[i0] = i0 == 0 ? 1.0 : 0.0;
+            if (i1 < n) Lm[i1] = 0.0;
             kd = 1;
         }
         if (lane == 0) {
@@ -1229,10 +1229,10 @@ __device__ __noinline__ void eigen_and_select(SlabShared<NW, PPW>& S, double* sm
         double* U = sm + L.oUnew[k];
         const int i0 = lane, i1 = lane + 32;
         for (int a = 0; a < rk; a++) {
-            double u0 = U[i0 + lu * a], u1 = i1 < nk ? U[i1 + lu * a] : 0.0;
+            double u0 = i0 < nk ? U[i0 + lu * a] : 0.0, u1 = i1 < nk ? U[i1 + lu * a] : 0.0;
             for (int rep = 0; rep < 2; rep++)
                 for (int b = 0; b < a; b++) {
-                    const double w0 = U[i0 + lu * b], w1 = i1 < nk ? U[i1 + lu * b] : 0.0;
+                    const double w0 = i0 < nk ? U[i0 + lu * b] : 0.0, w1 = i1 < nk ? U[i1 + lu * b] : 0.0;
                     double dot = u0 * w0 + u1 * w1;
                     for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
                     u0 -= dot * w0;
@@ -1241,7 +1241,7 @@ __device__ __noinline__ void eigen_and_select(SlabShared<NW, PPW>& S, double* sm
             double nn = u0 * u0 + u1 * u1;
             for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
             const double inv = nn > 0.0 ? rsqrt(nn) : 0.0;
-            U[i0 + lu * a] = u0 * inv;
+            if (i0 < nk) U[i0 + lu * a] = u0 * inv;
             if (i1 < nk) U[i1 + lu * a] = u1 * inv;
             __syncwarp();
         }
