@@ -771,7 +771,8 @@ def run_gpu_tucker(args):
                 if rank == 0:
                     sweep.append({"max_rank": r, "compr_err": eps, "tets_per_gpu": pt["config"]["tets_per_gpu"],
                                   "ms_per_step": pt["ms_per_step"], "value": pt["value"], "mean_rank_after": pt["config"]["mean_rank_after"],
-                                  "roofline_frac": pt["roofline"]["frac"], "executed_tflops": pt["roofline"]["executed_tflops"]})
+                                  "roofline_frac": pt["roofline"]["frac"], "executed_tflops": pt["roofline"]["executed_tflops"],
+                                  "kernel": pt["roofline"]["kernel"]})
     if rank == 0:
         line["vs_baseline"] = None
         line["clocks"] = clocks

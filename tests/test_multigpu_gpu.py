@@ -56,7 +56,7 @@ def test_partitioned_tucker_bit_identical():
     import torch
     n = torch.cuda.device_count()
     if n < 2:
-        return _virtual("test_virtual_ranks_tucker_bit_identical")
+        return _virtual("test_virtual_ranks_tucker_bit_identical", (12, 10, 8), 0, "general")
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29521", os.path.join(ROOT, "scripts", "mgpu_tucker_check.py")]

@@ -441,6 +441,17 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
                              reinterpret_cast<char*>(p.fn + (size_t)cur.tet * p.N);
             }
     }
+    // Halo push, upwind-select arithmetic: the peer that holds this tet as a ghost row reads it only where ITS
+    // v.n <= 0, i.e. where v.n_f >= 0 for the face f shared with that peer (the consumer-side inflow-half loads
+    // above, or the select `vn > 0 ? f : fa`).  So only that half of the row goes over NVLink — the union over
+    // the faces whose neighbour is a ghost row, with the guard band of the receiver's single-precision predicate.
+    // The expression-shape arithmetic reads the whole neighbour row: everything is pushed then.
+    bool ghostF[4] = {false, false, false, false};
+    if (GENERIC && UPWIND) {
+#pragma unroll
+        for (int f = 0; f < 4; f++) ghostF[f] = ((rec.ghostFaces >> f) & 1) != 0;
+    }
+    const double pushGuard = -(double)P.guard;
     double accDens = 0.0;
     double accWall[4] = {0.0, 0.0, 0.0, 0.0};
 
@@ -524,6 +535,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
             const double y1m[2] = {um.x, um.y}, y1p[2] = {up.x, up.y};
             const double z2m[2] = {pv[kk].x, pv[kk].y}, z2p[2] = {nx.x, nx.y};
             double out[2];
+            bool pushEl = !UPWIND;
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const double fv = fcv[u];
@@ -531,6 +543,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
                     const double vn = __dadd_rn(cxy[kk][f][u], tzf[f]);
+                    if (GENERIC && UPWIND && ghostF[f] && vn >= pushGuard) pushEl = true;
                     const double fau = u == 0 ? fa[f].x : fa[f].y;
                     if (!GENERIC || pairF[f]) {
                         if (UPWIND) {
@@ -561,7 +574,7 @@ __device__ __forceinline__ void item_compute(const BulkParams& P, const Smem& sm
             if (GENERIC) {
 #pragma unroll
                 for (int q = 0; q < 4; q++)
-                    if (pushOn[q]) *reinterpret_cast<double2*>(outp[kk] + pushOff[q]) = o;
+                    if (pushOn[q] && pushEl) *reinterpret_cast<double2*>(outp[kk] + pushOff[q]) = o;
             }
             outp[kk] += PB;
         }

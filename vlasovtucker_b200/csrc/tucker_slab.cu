@@ -82,7 +82,7 @@ __device__ __forceinline__ void warp_store(const double (&acc)[2], double* C, in
 struct SlabLay {
     int p[3], LU[3], LD, slab, rK;
     int oSlab[5];        // A ring (2), B, |v.n|, R / X
-    int oFac[3][3];      // operand s (0 neighbour, 1 |v.n|, 2 previous rhs / own f), factor k: LU[k] x rK
+    int oFac[3][3];      // operand s (0 neighbour, 1 |v.n|, 2 previous rhs / own f), factor k < 2: LU[k] x rK
     int oT[3];           // U0 M2 of operand s: LD x rK, double buffered
     int oM2[3];          // core x_3 U2(i2, :) of operand s: rK x rK, double buffered
     int oCore[3], coreCap;
@@ -106,9 +106,9 @@ __host__ __device__ inline SlabLay slab_layout(const int n[3], int rK)
         o += L.slab;
     }
     for (int s = 0; s < 3; s++)
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < 3; k++) {   // the third factor is read where it lies (one row per slab): nothing staged
             L.oFac[s][k] = o;
-            o += L.LU[k] * rK;
+            if (k < 2) o += L.LU[k] * rK;
         }
     for (int s = 0; s < 3; s++) {   // two sets (slab parity), the second one 3 LD rK further on
         L.oT[s] = o;
@@ -677,7 +677,7 @@ __device__ __noinline__ void stage_operands(SlabShared<NW, PPW>& S, double* sm)
     __syncthreads();
     for (int s = 0; s < 3; s++) {
         if (!S.op[s].on) continue;
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < 2; k++) {
             double* dst = sm + L.oFac[s][k];
             const double* src = S.op[s].U[k];
             const int lu = L.LU[k], nk = S.P.n[k], rk = S.op[s].r[k], ldu = S.op[s].ldu[k];
@@ -722,7 +722,7 @@ __device__ __noinline__ double pass1(SlabShared<NW, PPW>& S, double* sm)
     const bool prof = S.profOn && tid == 0;
     double* const Aglob = S.Aglob;
     double* const Xglob = S.Xglob;
-    const int tSet = 3 * LD * rK, mSet = 3 * rK * rK, lu1 = L.LU[1], lu2 = L.LU[2];
+    const int tSet = 3 * LD * rK, mSet = 3 * rK * rK, lu1 = L.LU[1];
     const bool on0 = S.op[0].on, on1 = S.op[1].on;
     const int K40 = on0 ? ceil4(S.op[0].r[1]) / 4 : 0, K41 = on1 ? ceil4(S.op[1].r[1]) / 4 : 0, K42 = ceil4(S.op[2].r[1]) / 4;
     const double vmin0 = S.P.vmin[0], vmin1 = S.P.vmin[1], st0 = S.P.step[0], st1 = S.P.step[1];
@@ -751,7 +751,8 @@ __device__ __noinline__ double pass1(SlabShared<NW, PPW>& S, double* sm)
             if (!S.op[s].on) continue;
             const int r0 = S.op[s].r[0], r1 = S.op[s].r[1], r2 = S.op[s].r[2];
             const int r0K = ceil4(r0), r1K = ceil8(r1);
-            const double* u2 = sm + L.oFac[s][2] + i2;
+            const double* u2 = S.op[s].U[2] + i2;   // global state / |v.n| table, or the previous rounding's factor in shared memory
+            const int lu2 = S.op[s].ldu[2];
             const double* core = S.op[s].core;
             double* M2 = sm + L.oM2[s] + set * mSet;
             for (int e = tid; e < r0K * r1K; e += T) {

@@ -188,6 +188,7 @@ void rebuild_tet_records(vt_ctx* ctx, vt::Species& sp)
             r.pushPeer[j] = sp.pushPeer.empty() ? -1 : sp.pushPeer[fi];
             r.pushRow[j] = sp.pushRow.empty() ? -1 : sp.pushRow[fi];
             r.nbr[j] = ctx->nbrHost[4 * (size_t)p + j];
+            if (r.nbr[j] >= ctx->nOwned) r.ghostFaces |= 1 << j;
             if (bc == VT_PBC_SOURCE) {
                 const int sid = sp.sourceId.empty() ? -1 : sp.sourceId[fi];
                 if (sid < 0 || sid >= sp.nSrc) throw std::invalid_argument("Source face without a source PDF");

@@ -32,7 +32,8 @@ struct TetRec {
     // new state there as well (peer index into StepParams::peerFn, row in the peer's buffer)
     int32_t pushPeer[4]; // -1 = unused
     int32_t pushRow[4];
-    int32_t pad[2];      // sizeof == 224: records are copied with 16-byte cp.async
+    int32_t ghostFaces;  // bit f: the neighbour across face f is a ghost row (owned by a peer): where v.n_f >= 0 that peer reads this tet
+    int32_t pad;         // sizeof == 224: records are copied with 16-byte cp.async
 };
 static_assert(sizeof(TetRec) == 224, "TetRec must stay a multiple of 16 bytes");
 
