@@ -1240,6 +1240,7 @@ int guard(F f)
 void tucker_materialize(vt_ctx* ctx, Species& sp)
 {
     TuckerState& ts = state_of(sp);
+    if (ts.densePending) tucker_from_dense(ctx, sp);   // rows uploaded since the last compression
     if (ts.denseValid) return;
     TuckerParams P;
     fill_params(ctx, sp, ts, P);
@@ -1253,9 +1254,29 @@ void tucker_materialize(vt_ctx* ctx, Species& sp)
 
 // Compress the dense rows in sp.f[sp.cur] into the Tucker state, exactly (precision 0) as
 // ParticleData<Tucker>::SetMaxwellPDF does (particle_data.cpp:64-69), ranks capped by the slot size.
+void tucker_begin_dense_write(vt_ctx* ctx, Species& sp)
+{
+    TuckerState& ts = state_of(sp);
+    if (!ts.densePending) tucker_materialize(ctx, sp);   // while an upload is pending the dense copy IS the state
+}
+
+void tucker_end_dense_write(vt_ctx*, Species& sp)
+{
+    TuckerState& ts = state_of(sp);
+    ts.densePending = true;
+    ts.denseValid = true;
+    sp.densityValid = false;
+}
+
+static void ensure_compressed(vt_ctx* ctx, Species& sp)
+{
+    if (state_of(sp).densePending) tucker_from_dense(ctx, sp);
+}
+
 void tucker_from_dense(vt_ctx* ctx, Species& sp)
 {
     TuckerState& ts = state_of(sp);
+    ts.densePending = false;
     TuckerParams P;
     fill_params(ctx, sp, ts, P);
     P.mode = 1;
@@ -1272,6 +1293,7 @@ void tucker_from_dense(vt_ctx* ctx, Species& sp)
 void tucker_push_current(vt_ctx* ctx, Species& sp)
 {
     TuckerState& ts = state_of(sp);
+    ensure_compressed(ctx, sp);
     if (ctx->nOwned == 0 || sp.nPeers == 0) return;
     if (ts.nPeers != sp.nPeers) throw std::runtime_error("partitioned Tucker species: vt_tucker_halo_attach has not been called");
     TuckerParams P;
@@ -1443,6 +1465,7 @@ int vt_tucker_get_ranks(vt_ctx* ctx, int species, int32_t* ranks)
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
         TuckerState& ts = state_of(sp);
+        ensure_compressed(ctx, sp);
         std::vector<int> r(3 * (size_t)ctx->nOwned);
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
         VT_CUDA(cudaMemcpy(r.data(), ts.ranks[ts.cur], r.size() * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1459,6 +1482,7 @@ int vt_tucker_get_factors(vt_ctx* ctx, int species, int tet, int32_t ranks[3], d
         VT_CUDA(cudaSetDevice(ctx->device));
         Species& sp = species_of(ctx, species);
         TuckerState& ts = state_of(sp);
+        ensure_compressed(ctx, sp);
         if (tet < 0 || tet >= ctx->nOwned) throw std::out_of_range("tet index");
         const int p = ctx->inv[tet];
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1519,6 +1543,7 @@ int vt_step_tucker(vt_ctx* ctx, int species, double dt, const double ext[3])
             throw std::runtime_error(std::to_string(sp.danglingFaces) + " boundary faces have no neighbour and no particle BC");
         if (sp.nPeers > 0 && ts.nPeers != sp.nPeers)
             throw std::runtime_error("partitioned Tucker species: vt_tucker_halo_attach has not been called");
+        ensure_compressed(ctx, sp);
         check_halo_status(ctx);
         ensure_vnabs(ctx, sp, ts);
         TuckerParams P;

@@ -28,6 +28,7 @@ struct TuckerState {
     int maxRank = 0;
     int cur = 0;
     bool vnabsValid = false;
+    bool densePending = false;   // rows were written into the dense copy (vt_species_set_pdf): re-compress before the next use
     int lastKernel = 0;          // 0 none yet, 1 k_tucker, 2 k_tucker_slab
     bool denseValid = false;     // sp.f[sp.cur] holds the reconstruction of buf[cur]
 };

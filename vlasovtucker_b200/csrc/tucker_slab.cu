@@ -1540,7 +1540,8 @@ bool slab_eligible(const vt_ctx* ctx, const TuckerParams& P)
     const int nmin = std::min({P.n[0], P.n[1], P.n[2]});
     // up to 32 nodes per axis the general kernel (four 128-thread CTAs per SM) is the faster one: measured 36.9 ms
     // against 52 ms for 3072 tets x 32^3 (profiles/r2_tucker_slab_notes.md)
-    if (nmax > kMaxP || nmax <= 32 || nmin < 2) return false;
+    static const int minN = std::getenv("VT_TUCKER_SLAB_MIN_N") ? std::atoi(std::getenv("VT_TUCKER_SLAB_MIN_N")) : 33;
+    if (nmax > kMaxP || nmax < minN || nmax <= 16 || nmin < 2) return false;
     if (!(P.eps > 0.0) || P.eps * P.eps / 3.0 < 1e-13) return false;   // small-eps refinement lives in k_tucker
     const int rK = rank_cols(P);
     if (rK > 16) return false;
@@ -1556,10 +1557,15 @@ void launch_tucker_slab(vt_ctx* ctx, TuckerState& ts, TuckerParams& P)
     const size_t smem = (size_t)L.total * sizeof(double);
     const int nmax = std::max({P.n[0], P.n[1], P.n[2]});
     const int sms = ctx->prop.multiProcessorCount;
-    (void)nmax;
-    const int grid = std::min({ctx->nOwned, ts.scratchCTAs, sms});
-    VT_CUDA(cudaFuncSetAttribute(k_tucker_slab<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tucker_slab<512, 4><<<grid, 512, smem, ctx->stream>>>(P);
+    if (nmax <= 32) {   // experiment (VT_TUCKER_SLAB_MIN_N <= 32): 256 threads, two CTAs per SM
+        const int grid = std::min({ctx->nOwned, ts.scratchCTAs, 2 * sms});
+        VT_CUDA(cudaFuncSetAttribute(k_tucker_slab<256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tucker_slab<256, 3><<<grid, 256, smem, ctx->stream>>>(P);
+    } else {
+        const int grid = std::min({ctx->nOwned, ts.scratchCTAs, sms});
+        VT_CUDA(cudaFuncSetAttribute(k_tucker_slab<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tucker_slab<512, 4><<<grid, 512, smem, ctx->stream>>>(P);
+    }
     ctx->launches++;
     VT_CUDA(cudaGetLastError());
 }

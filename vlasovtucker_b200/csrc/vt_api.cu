@@ -498,7 +498,7 @@ int vt_species_set_pdf(vt_ctx* ctx, int species, int first, int count, const dou
         vt::Species& sp = species_of(ctx, species);
         if (first < 0 || count < 0 || first + count > ctx->nOwned + ctx->nGhost)
             throw std::out_of_range("vt_species_set_pdf: tet range");
-        if (sp.tucker) vt::tucker_materialize(ctx, sp);   // partial ranges keep the other rows
+        if (sp.tucker) vt::tucker_begin_dense_write(ctx, sp);   // partial ranges keep the other rows
         double* dst = sp.f[sp.cur];
         const size_t rowB = (size_t)sp.N * sizeof(double);
         // ghost rows and identity order: straight copies
@@ -518,7 +518,7 @@ int vt_species_set_pdf(vt_ctx* ctx, int species, int first, int count, const dou
         }
         VT_CUDA(cudaStreamSynchronize(ctx->stream));
         sp.densityValid = false;
-        if (sp.tucker) vt::tucker_from_dense(ctx, sp);
+        if (sp.tucker) vt::tucker_end_dense_write(ctx, sp);
     });
 }
 

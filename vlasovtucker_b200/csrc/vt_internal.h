@@ -196,6 +196,11 @@ void launch_density(vt_ctx* ctx, Species& sp);
 void tucker_materialize(vt_ctx* ctx, Species& sp);
 // Tucker species: re-compress the dense rows in sp.f[sp.cur] into the Tucker state (precision 0)
 void tucker_from_dense(vt_ctx* ctx, Species& sp);
+// Tucker species, partial uploads (vt_species_set_pdf streams a snapshot in batches): make the dense copy current
+// before rows are written into it, and defer the re-compression until the state is used — one HOSVD pass over
+// the tets for the whole upload instead of one per batch
+void tucker_begin_dense_write(vt_ctx* ctx, Species& sp);
+void tucker_end_dense_write(vt_ctx* ctx, Species& sp);
 // Tucker species, multi-GPU: copy the current slots of the boundary tets into the peers' ghost rows
 void tucker_push_current(vt_ctx* ctx, Species& sp);
 void poisson_destroy(PoissonData* p);
