@@ -586,6 +586,45 @@ __device__ void jacobi_warp(const JacobiWork& ws, int k)
     }
 }
 
+// Per-thread plan of one slab copy global -> shared through cp.async: which 16-byte (8-byte for an odd n0) pieces
+// this thread moves.  Built once per pass, so that the index arithmetic — a division and a modulo per piece —
+// stays out of the slab loops.  Slab element (r, c), r < rows contiguous in both spaces, sits at shared r + LD c
+// and at global r + gStride c.
+template <int T>
+struct CopyPlan {
+    static constexpr int kMax = (kMaxP * kMaxP + T - 1) / T;
+    int n;
+    int soff[kMax], goff[kMax];
+    bool vec2;
+    __device__ __forceinline__ void build(int tid, int rows, int cols, int LD, int gStride)
+    {
+        vec2 = (rows % 2) == 0 && (gStride % 2) == 0;
+        const int w = vec2 ? rows / 2 : rows, total = w * cols, step = vec2 ? 2 : 1;
+        n = 0;
+#pragma unroll
+        for (int m = 0; m < kMax; m++) {
+            const int e = tid + T * m;
+            soff[m] = goff[m] = 0;
+            if (e < total) {
+                const int r = step * (e % w), c = e / w;
+                soff[m] = r + LD * c;
+                goff[m] = r + gStride * c;
+                n = m + 1;
+            }
+        }
+    }
+    __device__ __forceinline__ void issue(double* buf, const double* src) const
+    {
+#pragma unroll
+        for (int m = 0; m < kMax; m++) {
+            if (m < n) {
+                if (vec2) cp_async16(buf + soff[m], src + goff[m]);
+                else cp_async8(buf + soff[m], src + goff[m]);
+            }
+        }
+    }
+};
+
 enum { KIND_FACE = 0, KIND_ACCEL = 1, KIND_FINAL = 2 };
 
 // Everything the passes share, in SHARED memory.  With ~190 KB of shared memory in use the L1 cache is almost
@@ -729,6 +768,7 @@ __device__ __noinline__ double pass1(SlabShared<NW, PPW>& S, double* sm)
     const double coef = S.coef, nrm0 = S.nrm[0], nrm1 = S.nrm[1];
     const double g0 = S.gacc[0], g1 = S.gacc[1], g2 = S.gacc[2], dt = S.P.dt;
     double wallSum = 0.0;
+    // (a CopyPlan here costs more in spilled registers than the index arithmetic it saves: measured)
     auto issueA = [&](int j, double* buf) {
         const double* src = Aglob + (size_t)j * M;
         if (vec2) {
@@ -901,7 +941,6 @@ __device__ __noinline__ void gram_pass01(SlabShared<NW, PPW>& S, double* sm)
     const SlabLay& L = S.L;
     const int n0 = S.P.n[0], n1 = S.P.n[1], n2 = S.P.n[2], M = n0 * n1;
     const int p0 = L.p[0], p1 = L.p[1], LD = L.LD;
-    const bool vec2 = (n0 % 2) == 0;
     double* const ring0 = sm + L.oV[0];
     const int slabSz = L.slab;
     const double* const Xglob = S.Xglob;
@@ -932,15 +971,9 @@ __device__ __noinline__ void gram_pass01(SlabShared<NW, PPW>& S, double* sm)
                 offA[j] = offB[j] = kstep[j] = K[j] = 0;
             }
         }
-        auto issueS = [&](int j, double* buf) {
-            const double* src = Xglob + (size_t)j * M;
-            if (vec2) {
-                const int h0 = n0 / 2;
-                for (int e = tid; e < M / 2; e += T) cp_async16(buf + 2 * (e % h0) + LD * (e / h0), src + 2 * e);
-            } else {
-                for (int e = tid; e < M; e += T) cp_async8(buf + (e % n0) + LD * (e / n0), src + e);
-            }
-        };
+        CopyPlan<T> plan;
+        plan.build(tid, n0, n1, LD, n0);
+        auto issueS = [&](int j, double* buf) { plan.issue(buf, Xglob + (size_t)j * M); };
         issueS(0, ring0);
         cp_async_commit();
         if (n2 > 1) issueS(1, ring0 + slabSz);
@@ -987,7 +1020,6 @@ __device__ __noinline__ void gram_pass2(SlabShared<NW, PPW>& S, double* sm)
     const SlabLay& L = S.L;
     const int n0 = S.P.n[0], n1 = S.P.n[1], n2 = S.P.n[2], M = n0 * n1;
     const int p0 = L.p[0], LD = L.LD;
-    const bool vec2 = (n0 % 2) == 0;
     double* const ring0 = sm + L.oV[0];
     const int slabSz = L.slab;
     const double* const Xglob = S.Xglob;
@@ -1010,15 +1042,9 @@ __device__ __noinline__ void gram_pass2(SlabShared<NW, PPW>& S, double* sm)
             offB[j] = 4 * k0 + c + LD * (8 * J + g);
             K[j] = m == 15 ? 0 : (m == 0 ? Kh : K4 - Kh);
         }
-        auto issueC = [&](int i1, double* buf) {
-            const double* src = Xglob + (size_t)n0 * i1;
-            if (vec2) {
-                const int h0 = n0 / 2;
-                for (int e = tid; e < h0 * n2; e += T) cp_async16(buf + 2 * (e % h0) + LD * (e / h0), src + 2 * (e % h0) + (size_t)M * (e / h0));
-            } else {
-                for (int e = tid; e < n0 * n2; e += T) cp_async8(buf + (e % n0) + LD * (e / n0), src + (e % n0) + (size_t)M * (e / n0));
-            }
-        };
+        CopyPlan<T> plan;
+        plan.build(tid, n0, n2, LD, M);
+        auto issueC = [&](int i1, double* buf) { plan.issue(buf, Xglob + (size_t)n0 * i1); };
         issueC(0, ring0);
         cp_async_commit();
         if (n1 > 1) issueC(1, ring0 + slabSz);
@@ -1252,74 +1278,100 @@ __device__ __noinline__ void eigen_and_select(SlabShared<NW, PPW>& S, double* sm
 }
 
 // ---- pass 3: core = X x_1 U0^T x_2 U1^T x_3 U2^T, slab by slab; then the results of the rounding
-template <int T, int NW, int PPW>
+template <int T, int NW, int PPW, int RK>
 __device__ __noinline__ void pass3(SlabShared<NW, PPW>& S, double* sm, double wall0, double wall1, double wall2, double wall3)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const SlabLay& L = S.L;
     const int n0 = S.P.n[0], n1 = S.P.n[1], n2 = S.P.n[2], M = n0 * n1;
     const int p0 = L.p[0], p1 = L.p[1], LD = L.LD, rK = L.rK, nb1 = p1 / 8;
-    const bool vec2 = (n0 % 2) == 0;
-    constexpr int CPT = (16 * 16 * 16 + T - 1) / T;
-    double cacc[CPT];
-#pragma unroll
-    for (int j = 0; j < CPT; j++) cacc[j] = 0.0;
+    constexpr int CPT = (RK * RK * RK + T - 1) / T;
     const int r0 = S.rsel[0], r1 = S.rsel[1], r2 = S.rsel[2], cn = r0 * r1 * r2;
-    const int r0B = ceil8(r0) / 8, r1B = ceil8(r1) / 8;
-    const int LDP = rK + 4;
-    double* const Ps = slab_buf(sm, L, 4);
-    double* const Qs = sm + L.oT[0];
+    const int r0B = ceil8(r0) / 8;
     const double* const Xglob = S.Xglob;
     const int slabSz = L.slab;
+    const int lu0 = L.LU[0], lu1 = L.LU[1], lu2 = L.LU[2];
     for (int e = tid; e < 4 * slabSz; e += T) sm[e] = 0.0;
     __syncthreads();
-    auto issueX = [&](int j, double* buf) {
-        const double* src = Xglob + (size_t)j * M;
-        if (vec2) {
-            const int h0 = n0 / 2;
-            for (int e = tid; e < M / 2; e += T) cp_async16(buf + 2 * (e % h0) + LD * (e / h0), src + 2 * e);
-        } else {
-            for (int e = tid; e < M; e += T) cp_async8(buf + (e % n0) + LD * (e / n0), src + e);
-        }
-    };
+    CopyPlan<T> planX;
+    planX.build(tid, n0, n1, LD, n0);
+    auto issueX = [&](int j, double* buf) { planX.issue(buf, Xglob + (size_t)j * M); };
     issueX(0, sm);
     cp_async_commit();
     if (n2 > 1) issueX(1, sm + slabSz);
     cp_async_commit();
+    // W(a, i1, c) = sum over i2 of U2(i2, c) (U0^T S_i2)(a, i1), accumulated in REGISTERS over the slabs: a warp owns an
+    // 8 x 8 block (a-block I, i1-block J) of P = U0^T S — with one a-block the sum over i0 is split between two warps —
+    // computes it on the tensor cores and multiplies its two entries per lane into the r2 accumulators right away.
+    // No shared-memory round trip and no second barrier per slab; the partial sums meet in shared memory at the end.
+    const int KS = r0B == 1 ? 2 : 1;                 // warps per block along the contraction
+    const int nTask = r0B * nb1 * KS;                // <= 14 for grids up to 48 nodes and 16 warps
+    const bool mine = warp < nTask;
+    const int tI = mine ? warp % r0B : 0, tJ = mine ? (warp / r0B) % nb1 : 0, tK = mine ? warp / (r0B * nb1) : 0;
+    const int K4 = p0 / 4, kBeg = tK * ((K4 + KS - 1) / KS), kEnd = min(K4, kBeg + (K4 + KS - 1) / KS);
+    const int g = lane >> 2, c = lane & 3;
+    double wacc[2][RK];
+#pragma unroll
+    for (int q = 0; q < RK; q++) wacc[0][q] = wacc[1][q] = 0.0;
     {
-        const double* U0 = sm + L.oUnew[0];
-        const double* U1 = sm + L.oUnew[1];
+        const double* U0 = sm + L.oUnew[0] + lu0 * (8 * tI + g) + c;
         const double* U2 = sm + L.oUnew[2];
-        const int lu0 = L.LU[0], lu1 = L.LU[1], lu2 = L.LU[2];
         for (int i2 = 0; i2 < n2; i2++) {
             if (i2 + 2 < n2) issueX(i2 + 2, sm + ((i2 + 2) & 3) * slabSz);
             cp_async_commit();
             cp_async_wait<2>();
             __syncthreads();
-            const double* Sl = sm + (i2 & 3) * slabSz;
-            // P = U0^T S   (r0 x n1)
-            for (int task = warp; task < r0B * nb1; task += NW) {
-                const int I = task % r0B, J = task / r0B;
-                double c[2] = {0.0, 0.0};
-                warp_mma(c, U0 + lu0 * 8 * I, lu0, 1, Sl + LD * 8 * J, 1, LD, p0 / 4);
-                warp_store(c, Ps + 8 * I + LDP * (8 * J), 1, LDP);
-            }
-            __syncthreads();
-            // Q = P U1   (r0 x r1)
-            for (int task = warp; task < r0B * r1B; task += NW) {
-                const int I = task % r0B, J = task / r0B;
-                double c[2] = {0.0, 0.0};
-                warp_mma(c, Ps + 8 * I, 1, LDP, U1 + lu1 * 8 * J, 1, lu1, p1 / 4);
-                warp_store(c, Qs + 8 * I + rK * (8 * J), 1, rK);
-            }
-            __syncthreads();
+            if (!mine) continue;
+            const double* Sl = sm + (i2 & 3) * slabSz + c + LD * (8 * tJ + g);
+            double pacc[2] = {0.0, 0.0};
+            for (int kk = kBeg; kk < kEnd; kk++) dmma884(pacc, U0[4 * kk], Sl[4 * kk]);
 #pragma unroll
-            for (int j = 0; j < CPT; j++) {
-                const int e = tid + T * j;
-                if (e < cn) {
-                    const int a = e % r0, b = (e / r0) % r1, c = e / (r0 * r1);
-                    cacc[j] = fma(Qs[a + rK * b], U2[i2 + lu2 * c], cacc[j]);
+            for (int q = 0; q < RK; q++) {
+                if (q < r2) {
+                    const double u = U2[i2 + lu2 * q];
+                    wacc[0][q] = fma(pacc[0], u, wacc[0][q]);
+                    wacc[1][q] = fma(pacc[1], u, wacc[1][q]);
                 }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    // W to shared memory: Ws(a, i1, c) at a + rK (i1 + p1 c); the second half of a split sum is added to the first
+    double* const Ws = sm;
+    for (int half = 0; half < KS; half++) {
+        if (mine && tK == half) {
+            const int a = 8 * tI + g;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i1 = 8 * tJ + 2 * c + u;
+#pragma unroll
+                for (int q = 0; q < RK; q++) {
+                    if (q < r2) {
+                        double* dst = Ws + a + rK * (i1 + p1 * q);
+                        *dst = (half == 0 ? 0.0 : *dst) + wacc[u][q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // core(a, b, c) = sum over i1 of W(a, i1, c) U1(i1, b)
+    double cacc[CPT];
+    {
+        const double* U1 = sm + L.oUnew[1];
+#pragma unroll
+        for (int j = 0; j < CPT; j++) {
+            const int e = tid + T * j;
+            if (e < cn) {
+                const int a = e % r0, b = (e / r0) % r1, cc = e / (r0 * r1);
+                const double* w = Ws + a + rK * p1 * cc;
+                const double* u1 = U1 + lu1 * b;
+                double v = 0.0;
+                for (int i1 = 0; i1 < n1; i1++) v = fma(w[rK * i1], u1[i1], v);
+                cacc[j] = v;
+            } else {
+                cacc[j] = 0.0;
             }
         }
     }
@@ -1513,7 +1565,8 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) k_tucker_slab(const Tucke
             gram_pass2<T, NW, PPW>(S, sm);
             eigen_and_select<T, NW, PPW>(S, sm);
             if (prof) tp = clock64();
-            pass3<T, NW, PPW>(S, sm, wall0, wall1, wall2, wall3);
+            if (S.L.rK <= 8) pass3<T, NW, PPW, 8>(S, sm, wall0, wall1, wall2, wall3);
+            else pass3<T, NW, PPW, 16>(S, sm, wall0, wall1, wall2, wall3);
             if (prof) S.prof[4] += clock64() - tp;
         }
     }
