@@ -231,47 +231,58 @@ __device__ __forceinline__ void rotation_of(double gpq, double d, double invTr, 
 // needs only itself and the two rotations), to the rows of the idle indices and to V <- V J.
 // Ends when no index is active.  On exit the columns of V are the eigenvectors and the diagonal of G the
 // eigenvalues, both to the tolerance above.
+// Work split: matrix k belongs to the warps GW k .. GW k + GW - 1, GW = 5 of sixteen (the last warp only keeps the barriers).  What a
+// round costs is the length of the instruction stream of its slowest warp — about five cycles per instruction,
+// nothing else to overlap with — so each warp runs the code of ONE matrix (a version that staged the loads of
+// all three matrices in every warp for more instruction-level parallelism took 2.4x as long per round).
 template <int T>
 __device__ void jacobi3(const JacobiWork& wShared)
 {
-    constexpr int NW = T / 32;
+    constexpr int GW = (T / 32) / 3;   // warps per matrix: five of sixteen (two of eight in the 256-thread instance)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const JacobiWork w = wShared;   // private copy: pointers and sizes in registers instead of a shared-memory load per use
+    const int k = warp / GW < 3 ? warp / GW : 2, wg = warp % GW;
+    const bool member = warp < 3 * GW;
+    const JacobiWork& w = wShared;
+    const int n = w.n[k], ld = w.ld[k], pk = w.p[k];
+    double* const G = w.G[k];
+    double* const V = w.V[k];
+    int* const act = w.act + 64 * k;
+    double* const rotC = w.rotC + kMaxSlots * k;
+    double* const rotS = w.rotS + kMaxSlots * k;
+    int* const rotPQ = w.rotPQ + kMaxSlots * k;
+    const double crit[3] = {w.crit[3 * k], w.crit[3 * k + 1], w.crit[3 * k + 2]};
+    const double invTr = w.invTr[k];
     long long* const wprof = tid == 0 ? w.prof : nullptr;
     for (int sweep = 0; sweep < kMaxSweeps; sweep++) {
         long long tj = wprof ? clock64() : 0;
         if (wprof && sweep == 0)
             for (int q = 18; q < 24; q++) wprof[q] = 0;
-        // ---- active sets
+        // ---- active sets: rows wg, wg + 5, ... of matrix k, the lanes share the columns
         if (tid < 6) w.mask[tid] = 0;
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int i = tid & 63, n = w.n[k], ld = w.ld[k];
-            if (i >= n) continue;
-            const double* G = w.G[k];
-            const double gii = G[i + ld * i];
-            bool hit = false;
-            for (int q = tid >> 6; q < n; q += T / 64)
-                if (q != i) hit |= needs_rotation(G[i + ld * q], gii, G[q + ld * q], w.crit + 3 * k);
-            if (hit) atomicOr(w.mask + 2 * k + (i >> 5), 1u << (i & 31));
+        if (member) {
+            for (int i = wg; i < n; i += GW) {
+                const double gii = G[i + ld * i];
+                bool hit = false;
+                for (int q = lane; q < n; q += 32)
+                    if (q != i) hit |= needs_rotation(G[i + ld * q], gii, G[q + ld * q], crit);
+                if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(w.mask + 2 * k + (i >> 5), 1u << (i & 31));
+            }
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            if (warp != k) continue;
+        if (member && wg == 0) {
             unsigned m0 = w.mask[2 * k], m1 = w.mask[2 * k + 1];
             int na = __popc(m0) + __popc(m1);
             if (na & 1) {   // an idle index completes the last pair (it exists: the padded dimension is even)
                 int d = 0;
-                while (d < w.p[k] && ((d < 32 ? m0 >> d : m1 >> (d - 32)) & 1u)) d++;
+                while (d < pk && ((d < 32 ? m0 >> d : m1 >> (d - 32)) & 1u)) d++;
                 if (d < 32) m0 |= 1u << d;
                 else m1 |= 1u << (d - 32);
                 na++;
             }
             const unsigned below = (1u << lane) - 1u;
-            if ((m0 >> lane) & 1u) w.act[64 * k + __popc(m0 & below)] = lane;
-            if ((m1 >> lane) & 1u) w.act[64 * k + __popc(m0) + __popc(m1 & below)] = 32 + lane;
+            if ((m0 >> lane) & 1u) act[__popc(m0 & below)] = lane;
+            if ((m1 >> lane) & 1u) act[__popc(m0) + __popc(m1 & below)] = 32 + lane;
             if (lane == 0) {
                 w.na[k] = na;
                 w.mask[2 * k] = m0;
@@ -279,58 +290,49 @@ __device__ void jacobi3(const JacobiWork& wShared)
             }
         }
         __syncthreads();
-        const int na0 = w.na[0], na1 = w.na[1], na2 = w.na[2];
-        const int maxRounds = max(na0, max(na1, na2)) - 1;
+        const int na = w.na[k];
+        const int maxRounds = max(w.na[0], max(w.na[1], w.na[2])) - 1;
         if (maxRounds <= 0) break;
+        const unsigned m0 = w.mask[2 * k], m1 = w.mask[2 * k + 1];
+        const int h = na >> 1;
         if (wprof) {
-            if (sweep < 6) wprof[18 + sweep] = na0 | (na1 << 8) | (na2 << 16);   // the last eigen-problem's active sets
+            if (sweep < 6) wprof[18 + sweep] = w.na[0] | (w.na[1] << 8) | (w.na[2] << 16);   // the last eigen-problem's active sets
             wprof[13] += maxRounds;
             wprof[14] += 1;
             const long long now = clock64();
             wprof[15] += now - tj;
             tj = now;
         }
-        // who am I in phase 2: rows x = tid & 63 of V (and of G when x is idle), starting with pair tid >> 6
-        const int x = tid & 63;
-        bool idle[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) idle[k] = ((x < 32 ? w.mask[2 * k] >> x : w.mask[2 * k + 1] >> (x - 32)) & 1u) == 0;
         for (int s = 0; s < maxRounds; s++) {
+            const bool live = member && s < na - 1;
             // ---- phase 1
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                if (warp != k) continue;
-                const int na = k == 0 ? na0 : (k == 1 ? na1 : na2), h = na >> 1;
-                if (lane < h && s < na - 1) {
-                    int a, b;
-                    if (lane == 0) {
-                        a = na - 1;
-                        b = s;
-                    } else {
-                        a = s + lane;
-                        if (a >= na - 1) a -= na - 1;
-                        b = s - lane;
-                        if (b < 0) b += na - 1;
-                    }
-                    int p = w.act[64 * k + a], q = w.act[64 * k + b];
-                    if (p > q) {
-                        const int xx = p;
-                        p = q;
-                        q = xx;
-                    }
-                    const int ld = w.ld[k];
-                    const double* G = w.G[k];
-                    const double gpq = G[p + ld * q], gpp = G[p + ld * p], gqq = G[q + ld * q];
-                    double c = 1.0, sn = 0.0;
-                    int rotated = 0;
-                    if (needs_rotation(gpq, gpp, gqq, w.crit + 3 * k)) {
-                        rotation_of(gpq, gqq - gpp, w.invTr[k], c, sn);
-                        rotated = 1;
-                    }
-                    w.rotC[kMaxSlots * k + lane] = c;
-                    w.rotS[kMaxSlots * k + lane] = sn;
-                    w.rotPQ[kMaxSlots * k + lane] = p | (q << 8) | (rotated << 16);
+            if (live && wg == 0 && lane < h) {
+                int a, b;
+                if (lane == 0) {
+                    a = na - 1;
+                    b = s;
+                } else {
+                    a = s + lane;
+                    if (a >= na - 1) a -= na - 1;
+                    b = s - lane;
+                    if (b < 0) b += na - 1;
                 }
+                int p = act[a], q = act[b];
+                if (p > q) {
+                    const int xx = p;
+                    p = q;
+                    q = xx;
+                }
+                const double gpq = G[p + ld * q], gpp = G[p + ld * p], gqq = G[q + ld * q];
+                double c = 1.0, sn = 0.0;
+                int rotated = 0;
+                if (needs_rotation(gpq, gpp, gqq, crit)) {
+                    rotation_of(gpq, gqq - gpp, invTr, c, sn);
+                    rotated = 1;
+                }
+                rotC[lane] = c;
+                rotS[lane] = sn;
+                rotPQ[lane] = p | (q << 8) | (rotated << 16);
             }
             __syncthreads();
             if (wprof) {
@@ -338,109 +340,54 @@ __device__ void jacobi3(const JacobiWork& wShared)
                 wprof[16] += now - tj;
                 tj = now;
             }
-            // ---- phase 2.  The three matrices are independent: every step below is written as "all loads of the
-            // three, then the arithmetic, then the stores", so that the latencies of the three overlap.
-            {
-                // 2x2 blocks: lane = pair i, warp (+ NW) = pair j
-                const int hmax = (max(na0, max(na1, na2))) >> 1;
-                for (int jb = 0; jb < hmax; jb += NW) {
-                    const int j = jb + warp, i = lane;
-                    bool on[3];
-                    int P[3], Q[3], R[3], S[3];
-                    double ci[3], si[3], cj[3], sj[3], m[3][4];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const int na = k == 0 ? na0 : (k == 1 ? na1 : na2), h = na >> 1, base = kMaxSlots * k;
-                        on[k] = s < na - 1 && j < h && i <= j;
-                        const int pqi = on[k] ? w.rotPQ[base + i] : 0, pqj = on[k] ? w.rotPQ[base + j] : 0;
-                        on[k] = on[k] && ((pqi | pqj) >> 16) != 0;
-                        P[k] = pqi & 255;
-                        Q[k] = (pqi >> 8) & 255;
-                        R[k] = pqj & 255;
-                        S[k] = (pqj >> 8) & 255;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        if (!on[k]) continue;
-                        const int base = kMaxSlots * k, ld = w.ld[k];
-                        const double* G = w.G[k];
-                        ci[k] = w.rotC[base + i];
-                        si[k] = w.rotS[base + i];
-                        cj[k] = w.rotC[base + j];
-                        sj[k] = w.rotS[base + j];
-                        m[k][0] = G[P[k] + ld * R[k]];
-                        m[k][1] = G[P[k] + ld * S[k]];
-                        m[k][2] = G[Q[k] + ld * R[k]];
-                        m[k][3] = G[Q[k] + ld * S[k]];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        if (!on[k]) continue;
-                        const int ld = w.ld[k];
-                        double* G = w.G[k];
-                        // M <- J_i^T M J_j   (for the diagonal block this annihilates g_PQ up to the accuracy of the rotation)
-                        const double nPR = cj[k] * m[k][0] - sj[k] * m[k][1], nPS = sj[k] * m[k][0] + cj[k] * m[k][1];
-                        const double nQR = cj[k] * m[k][2] - sj[k] * m[k][3], nQS = sj[k] * m[k][2] + cj[k] * m[k][3];
-                        const double oPR = ci[k] * nPR - si[k] * nQR, oQR = si[k] * nPR + ci[k] * nQR;
-                        const double oPS = ci[k] * nPS - si[k] * nQS, oQS = si[k] * nPS + ci[k] * nQS;
-                        if (i == j) {   // rows and columns are the same pair: P = R, Q = S; what is left of g_PQ is kept
-                            G[P[k] + ld * P[k]] = oPR;
-                            G[Q[k] + ld * Q[k]] = oQS;
-                            G[P[k] + ld * Q[k]] = oPS;
-                            G[Q[k] + ld * P[k]] = oPS;
-                        } else {
-                            G[P[k] + ld * R[k]] = oPR;
-                            G[R[k] + ld * P[k]] = oPR;
-                            G[P[k] + ld * S[k]] = oPS;
-                            G[S[k] + ld * P[k]] = oPS;
-                            G[Q[k] + ld * R[k]] = oQR;
-                            G[R[k] + ld * Q[k]] = oQR;
-                            G[Q[k] + ld * S[k]] = oQS;
-                            G[S[k] + ld * Q[k]] = oQS;
-                        }
+            // ---- phase 2
+            if (live) {
+                // 2x2 blocks: lane = pair i, warp of the group (+ 5) = pair j
+                for (int j = wg; j < h; j += GW) {
+                    const int i = lane;
+                    if (i > j) continue;
+                    const int pqi = rotPQ[i], pqj = rotPQ[j];
+                    if (((pqi | pqj) >> 16) == 0) continue;
+                    const int P = pqi & 255, Q = (pqi >> 8) & 255, R = pqj & 255, S = (pqj >> 8) & 255;
+                    const double ci = rotC[i], si = rotS[i], cj = rotC[j], sj = rotS[j];
+                    const double mPR = G[P + ld * R], mPS = G[P + ld * S], mQR = G[Q + ld * R], mQS = G[Q + ld * S];
+                    const double nPR = cj * mPR - sj * mPS, nPS = sj * mPR + cj * mPS;
+                    const double nQR = cj * mQR - sj * mQS, nQS = sj * mQR + cj * mQS;
+                    const double oPR = ci * nPR - si * nQR, oQR = si * nPR + ci * nQR;
+                    const double oPS = ci * nPS - si * nQS, oQS = si * nPS + ci * nQS;
+                    if (i == j) {   // rows and columns are the same pair; what is left of g_PQ is kept: the similarity stays exact
+                        G[P + ld * P] = oPR;
+                        G[Q + ld * Q] = oQS;
+                        G[P + ld * Q] = oPS;
+                        G[Q + ld * P] = oPS;
+                    } else {
+                        G[P + ld * R] = oPR;
+                        G[R + ld * P] = oPR;
+                        G[P + ld * S] = oPS;
+                        G[S + ld * P] = oPS;
+                        G[Q + ld * R] = oQR;
+                        G[R + ld * Q] = oQR;
+                        G[Q + ld * S] = oQS;
+                        G[S + ld * Q] = oQS;
                     }
                 }
                 // rows: V <- V J, and G(x, .) of the idle indices x
-                for (int jb = 0; jb < hmax; jb += T / 64) {
-                    const int j = jb + (tid >> 6);
-                    bool on[3];
-                    int P[3], Q[3];
-                    double c[3], sn[3], vp[3], vq[3], gp[3], gq[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const int na = k == 0 ? na0 : (k == 1 ? na1 : na2), h = na >> 1;
-                        on[k] = s < na - 1 && j < h && x < w.n[k];
-                        const int pq = on[k] ? w.rotPQ[kMaxSlots * k + j] : 0;
-                        on[k] = on[k] && (pq >> 16) != 0;
-                        P[k] = pq & 255;
-                        Q[k] = (pq >> 8) & 255;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        if (!on[k]) continue;
-                        const int ld = w.ld[k];
-                        c[k] = w.rotC[kMaxSlots * k + j];
-                        sn[k] = w.rotS[kMaxSlots * k + j];
-                        vp[k] = w.V[k][x + ld * P[k]];
-                        vq[k] = w.V[k][x + ld * Q[k]];
-                        if (idle[k]) {
-                            gp[k] = w.G[k][x + ld * P[k]];
-                            gq[k] = w.G[k][x + ld * Q[k]];
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        if (!on[k]) continue;
-                        const int ld = w.ld[k];
-                        w.V[k][x + ld * P[k]] = c[k] * vp[k] - sn[k] * vq[k];
-                        w.V[k][x + ld * Q[k]] = sn[k] * vp[k] + c[k] * vq[k];
-                        if (idle[k]) {
-                            const double np = c[k] * gp[k] - sn[k] * gq[k], nq = sn[k] * gp[k] + c[k] * gq[k];
-                            double* G = w.G[k];
-                            G[x + ld * P[k]] = np;
-                            G[P[k] + ld * x] = np;
-                            G[x + ld * Q[k]] = nq;
-                            G[Q[k] + ld * x] = nq;
+                for (int j = wg; j < h; j += GW) {
+                    const int pq = rotPQ[j];
+                    if ((pq >> 16) == 0) continue;
+                    const int P = pq & 255, Q = (pq >> 8) & 255;
+                    const double c = rotC[j], sn = rotS[j];
+                    for (int x = lane; x < n; x += 32) {
+                        const double vp = V[x + ld * P], vq = V[x + ld * Q];
+                        V[x + ld * P] = c * vp - sn * vq;
+                        V[x + ld * Q] = sn * vp + c * vq;
+                        if (((x < 32 ? m0 >> x : m1 >> (x - 32)) & 1u) == 0) {
+                            const double gp = G[x + ld * P], gq = G[x + ld * Q];
+                            const double np = c * gp - sn * gq, nq = sn * gp + c * gq;
+                            G[x + ld * P] = np;
+                            G[P + ld * x] = np;
+                            G[x + ld * Q] = nq;
+                            G[Q + ld * x] = nq;
                         }
                     }
                 }
