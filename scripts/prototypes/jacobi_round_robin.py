@@ -1,6 +1,7 @@
-"""CPU statement of the parallel two-sided Jacobi method of csrc/tucker_slab.cu (jacobi3): circle-method
+"""CPU statement of the parallel two-sided Jacobi method of csrc/tucker_slab.cu (jacobi3, jacobi_warp): circle-method
 pairing, one rotation per pair and round, G <- J^T G J applied 2x2-block pair by block pair over the upper
-triangle with a mirrored write, V <- V J; absolute + relative skip threshold.  Checks eigenvalues and
+triangle with a mirrored write, V <- V J; absolute + relative skip threshold (the device code adds the
+tolerance-aware criterion, the active-index sets and the pivoted Cholesky reduction in front).  Checks eigenvalues and
 eigenvectors against numpy.linalg.eigh on Gram matrices like the ones the Tucker rounding sees."""
 import numpy as np
 
@@ -77,8 +78,8 @@ def jacobi(G, max_sweeps=30):
     return np.diag(A)[:n].copy(), V[:n, :n].copy(), sweeps, rounds_with_work
 
 
-def gram_cases(rng):
-    for n in (48, 33, 24, 17):
+def gram_cases(rng, sizes=(48, 33, 24, 17)):
+    for n in sizes:
         # smooth, quickly decaying spectrum: unfolding of a sum of shifted Maxwellians
         x = np.linspace(-4, 4, n)
         X = sum(np.exp(-(x[:, None, None] - a) ** 2 - 1.3 * (x[None, :, None] - b) ** 2 - 0.7 * (x[None, None, :] - c) ** 2)
@@ -93,10 +94,10 @@ def gram_cases(rng):
         yield f"zero n={n}", np.zeros((n, n))
 
 
-def main():
+def main(sizes=(48, 33, 24, 17)):
     rng = np.random.default_rng(1)
     worst = 0.0
-    for name, G in gram_cases(rng):
+    for name, G in gram_cases(rng, sizes):
         lam, V, sweeps, work = jacobi(G)
         n = G.shape[0]
         tr = max(np.trace(G), 1e-300)

@@ -19,3 +19,11 @@ def test_leading_eigenpairs_prototype_matches_numpy(capsys):
     mod.main()
     out = capsys.readouterr().out
     assert out.startswith("cases 270")
+
+
+def test_round_robin_jacobi_statement_matches_numpy(capsys):
+    """The parallel two-sided Jacobi method of csrc/tucker_slab.cu, stated on the CPU (round-robin pairing, 2x2 block
+    updates with mirrored writes): eigenvalues, orthogonality and residuals against numpy on Gram matrices."""
+    mod = _load("jacobi_round_robin")
+    mod.main(sizes=(17, 12))
+    assert capsys.readouterr().out.rstrip().endswith("ok")

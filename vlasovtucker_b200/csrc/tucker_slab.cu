@@ -2,23 +2,27 @@
 // six Compress calls (src/tucker.cpp:66-98, rank rule :442-465) evaluated as truncated HOSVDs of the
 // dense sums (the formulation of tucker.cu, see its header), restructured for the machine:
 //
-//   * a CTA owns a tet for the whole step; dense data only ever exists as ONE velocity slab X(:,:,i2)
-//     in shared memory (plus the rounding's input X and the tet's own f in an L2-sized global scratch);
-//     every Tucker operand (the neighbour, |v.n| of the face, the previous rounded right-hand side) is
-//     re-expanded slab by slab from its factors staged in shared memory
-//   * every contraction runs on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA): the slab
-//     expansions T U1^T, the Gram matrices S S^T / S^T S (upper triangle of 8x8 blocks, accumulators
-//     live in registers across all slabs of a pass), the projections U0^T S and P U1
-//   * the three symmetric eigen-problems of a rounding are solved TOGETHER by the whole CTA with a
-//     parallel two-sided Jacobi method (round-robin ordering: n/2 disjoint rotations per round, every
-//     2x2 block pair of G is updated independently, two barriers per round) instead of one warp per
-//     matrix running a serial QL iteration
+//   * a 512-thread CTA (one per SM) owns a tet for the whole step; dense data only ever exist as ONE velocity
+//     slab in shared memory; the rounding's input X and the tet's own f live in a per-CTA global scratch
+//     (L2-sized), every Tucker operand (the neighbour, |v.n| of the face, the previous rounded right-hand
+//     side) is re-expanded slab by slab from its factors
+//   * every contraction runs on the FP64 tensor cores (mma.sync.m8n8k4.f64, SASS DMMA): the slab expansions
+//     (U0 M2) U1^T, the Gram matrices S S^T / S^T S / C^T C (upper triangle of 8x8 blocks, accumulators in
+//     registers for a whole pass), the projection U0^T S
+//   * the three symmetric eigen-problems of a rounding are first reduced by a pivoted Cholesky factorisation
+//     (the Gram matrix of a smooth tensor has numerical rank 12-36 of 48) and then solved by a parallel
+//     two-sided Jacobi method that only rotates where it matters for a rounding of relative error eps
 //
 // Passes of one rounding (X = what the reference rounds at this point):
-//   1  i2 slabs:  expand operands -> X slab (flux / acceleration / Euler update) -> store X, G0 += S S^T, G1 += S^T S
-//   2  i1 slabs of X (n0 x n2):  G2 += C^T C
-//   -  Jacobi on G0, G1, G2; rank rule; factors
-//   3  i2 slabs of X:  core += ((U0^T S) U1) (x) U2(i2, :)
+//   1  i2 slabs:  T = U0 M2 of every operand, then per 8x8 block: expand all operands into accumulator fragments and
+//                 combine them in registers (flux / acceleration / Euler update) -> X to the scratch; one barrier per slab
+//   G  i2 slabs of X: G0 += S S^T, G1 += S^T S;  i1 slabs of X (n0 x n2): G2 += C^T C
+//   E  pivoted Cholesky G = L L^T, Jacobi on L^T L, U = L W Lambda^(-1/2), rank rule (tucker.cpp:450-461)
+//   3  i2 slabs of X:  W += U2(i2, :) (x) (U0^T S) in registers, then core = W x_2 U1^T
+//
+// Shared memory: ~190 KB dynamic (+9 KB static), so the L1 is almost gone and anything on the stack costs an L2
+// round trip: kernel parameters, layout and operand descriptors live in shared memory and every pass is its
+// own __noinline__ function.  profiles/r2_tucker_slab_notes.md has the measurement trail.
 //
 // Served here: compression errors that do not need the small-eps refinement of tucker.cu (eps >= 5.5e-7),
 // grids of 33..48 nodes per axis, rank caps <= 16.  Everything else stays on k_tucker.
@@ -174,9 +178,8 @@ struct JacobiWork {
     double* V[3];
     double* W[3];
     int n[3], p[3], ld[3];
-    double* rotC;        // [3][kMaxSlots] rotation of a slot: cosine, sine, tangent
+    double* rotC;        // [3][kMaxSlots] rotation of a slot: cosine, sine
     double* rotS;
-    double* rotT;
     int* rotPQ;          // p | q << 8 | rotated << 16
     int* act;            // [3][64] indices that still have an off-diagonal entry above the threshold
     int* na;             // [3] their number (made even with an idle index)
@@ -598,7 +601,7 @@ struct SlabShared {
     double lam[3][kMaxN];
     int ord[3][kMaxN];
     int rsel[3];
-    double rotC[3 * kMaxSlots], rotS[3 * kMaxSlots], rotT[3 * kMaxSlots];
+    double rotC[3 * kMaxSlots], rotS[3 * kMaxSlots];
     int rotPQ[3 * kMaxSlots];
     int act[3 * 64], na[3];
     unsigned mask[6];
@@ -1430,7 +1433,6 @@ __global__ void __launch_bounds__(T, T >= 512 ? 1 : 2) k_tucker_slab(const Tucke
         }
         jw.rotC = S.rotC;
         jw.rotS = S.rotS;
-        jw.rotT = S.rotT;
         jw.rotPQ = S.rotPQ;
         jw.act = S.act;
         jw.na = S.na;
