@@ -355,3 +355,25 @@ def test_kuhn_box_full_size_properties(vt):
     ctx.step_full(g, 1e-3)
     assert np.array_equal(ctx.get_pdf(g), 4.0 * fa1)
     ctx.close()
+
+
+@pytest.mark.parametrize("n,chunk", [((48, 48, 4), None), ((40, 40, 6), 3), ((36, 44, 5), None), ((50, 50, 3), None)])
+def test_eight_warp_instances_for_planes_above_32x32(vt, oracle_mod, monkeypatch, n, chunk):
+    """VT_STEP_WIDE8=1 (opt-in): planes above 32x32 on eight consumer warps with three to five columns per thread and
+    consumer-side inflow-half neighbour loads — instead of the sixteen-warp instances, which spill from three columns
+    on.  Same arithmetic with explicit roundings: parity with the oracle as every other instance, on a mesh with
+    wall faces (the boundary instance) and with planes that do not fill the last column of every thread."""
+    monkeypatch.setenv("VT_STEP_WIDE8", "1")
+    m = oracle_mod.Mesh.load(mesh_path("rectangle_fine.msh"), [(3, 4), (5, 6)])
+    vmin, vmax = [-3, -0.1, -0.2], [3, 0.1, 0.2]
+    f0 = _smooth_state(m, n, vmin, vmax)
+    rng = np.random.default_rng(7)
+    E = rng.standard_normal((m.nTets, 3)) * 0.5
+    spec = {1: ("Absorbing", True), 2: ("Free", False)}
+    s, sp, ctx, g = _run_pair(vt, oracle_mod, m, n, vmin, vmax, 1.0, 10.0, f0, E, 1e-4, 3, bc_spec=spec, chunk=chunk, variant=64)
+    for _ in range(3):
+        s.update_pdf(sp, E)
+        ctx.step_full(g, 1e-4)
+    assert rel_l2(ctx.get_pdf(g), s.get_pdf(sp)) <= TOL
+    assert rel_l2(ctx.density(g), s.density(sp)) <= TOL
+    ctx.close()

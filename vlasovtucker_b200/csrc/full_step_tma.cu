@@ -693,9 +693,11 @@ __global__ void __launch_bounds__(NCW * 32 + kAuxThreads, 1) k_full_step_bulk(co
         col[kk].dFlB = 8u * (uint32_t)(2 * cv + ((i0 == 0) ? (p.n0 - 1) : -1));
         col[kk].dFrB = 8u * (uint32_t)(2 * cv + 1 + ((i0 + 2 == p.n0) ? -(p.n0 - 1) : 1));
         oEv[kk] = (SPEC && kk == 1) ? col[0].evB + SN * 8 : col[kk].evB;
-        vf[kk][0] = fmaf((float)i0, P.step0f, P.vmin0f);
-        vf[kk][1] = fmaf((float)(i0 + 1), P.step0f, P.vmin0f);
-        vf[kk][2] = fmaf((float)i1, P.step1f, P.vmin1f);
+        // a column beyond the plane (the last columns of a thread when the plane is not a multiple of the thread
+        // count) must never request neighbour values: NaN makes the load predicate false whatever the normal is
+        vf[kk][0] = col[kk].on ? fmaf((float)i0, P.step0f, P.vmin0f) : __int_as_float(0x7fc00000);
+        vf[kk][1] = col[kk].on ? fmaf((float)(i0 + 1), P.step0f, P.vmin0f) : __int_as_float(0x7fc00000);
+        vf[kk][2] = col[kk].on ? fmaf((float)i1, P.step1f, P.vmin1f) : __int_as_float(0x7fc00000);
     }
     ConsRings R;
     R.own = smem_u32(sm.ownRing);
@@ -773,11 +775,16 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
     const int PV = PE / 2;
     // variant bit 5: eight consumer warps with two columns per thread instead of sixteen with one
     const bool wide = (ctx->variant & 32) != 0 && PV == 512 && n1 % 2 == 0 && 256 % (n0 / 2) == 0;
-    const int ncw = wide ? 8 : 16;
+    // planes above 32x32 (up to 50x50): also eight consumer warps, three to five columns per thread in the generic
+    // column mapping — the sixteen-warp instances are capped at 96 registers per thread and spill from three
+    // columns on (cuobjdump -res-usage: 96-528 bytes of stack), eight warps get 232 after the register re-split.
+    // Opt-in (VT_STEP_WIDE8=1) until it has seen the whole parity suite.
+    const bool wide8 = (ctx->variant & 32) != 0 && !wide && PV > 2 * 256 && PV <= 5 * 256 && std::getenv("VT_STEP_WIDE8") != nullptr;
+    const int ncw = (wide || wide8) ? 8 : 16;
     const int kpt = (PV + ncw * 32 - 1) / (ncw * 32);
-    if (kpt > 4) return false;
+    if (kpt > (wide8 ? 5 : 4)) return false;
     // variant bit 7 switches the consumer-side neighbour loads off (whole neighbour planes by bulk copy)
-    const bool nbrSelf = upwind && wide && !(ctx->variant & 128);
+    const bool nbrSelf = upwind && (wide || wide8) && !(ctx->variant & 128);
     const size_t PB = (size_t)PE * 8;
     const size_t fixed = kItemRing * (sizeof(TetRec) + sizeof(ItemHdr)) + (4 * kMaxRing + 2 * kItemRing) * 8 + 128;
     const size_t maxSmem = 227 * 1024;
@@ -850,6 +857,21 @@ bool launch_full_step_tma(vt_ctx* ctx, Species& sp, StepParams& p, bool upwind, 
             if (nbrSelf && S == 4) launch_cfg<2, 8, 0, 4>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
             else if (nbrSelf && S == 2) launch_cfg<2, 8, 0, 2>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
             else launch_cfg<2, 8, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+        } else if (wide8) {
+            const int nbd = nbrSelf ? S : 0;   // S is 4 or 2 here
+            if (kpt == 3) {
+                if (nbd == 4) launch_cfg<3, 8, 0, 4>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+                else if (nbd == 2) launch_cfg<3, 8, 0, 2>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+                else launch_cfg<3, 8, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+            } else if (kpt == 4) {
+                if (nbd == 4) launch_cfg<4, 8, 0, 4>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+                else if (nbd == 2) launch_cfg<4, 8, 0, 2>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+                else launch_cfg<4, 8, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+            } else {
+                if (nbd == 4) launch_cfg<5, 8, 0, 4>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+                else if (nbd == 2) launch_cfg<5, 8, 0, 2>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+                else launch_cfg<5, 8, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
+            }
         } else if (kpt == 1) launch_cfg<1, 16, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
         else if (kpt == 2) launch_cfg<2, 16, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
         else if (kpt == 3) launch_cfg<3, 16, 0, 0>(ctx, P, upwind, allFast, smem, stream, maxCTAs);
