@@ -12,7 +12,10 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build", "obj")
 LIB = os.path.join(LIBDIR, "libvt_b200.so")
-SOURCES = ["vt_api.cu", "full_step.cu", "full_step_tma.cu", "poisson.cu", "halo.cu", "tucker.cu", "tucker_slab.cu", "group.cu"]
+# (source, object, extra flags): the general Tucker kernel is compiled once per instantiation (three objects from tucker_inst.cu)
+SOURCES = ["vt_api.cu", "full_step.cu", "full_step_tma.cu", "poisson.cu", "halo.cu", "tucker.cu", "tucker_slab.cu", "group.cu",
+           ("tucker_inst.cu", "tucker_inst64.o", ["-DVT_TUCKER_NM=64"]), ("tucker_inst.cu", "tucker_inst32.o", ["-DVT_TUCKER_NM=32"]),
+           ("tucker_inst.cu", "tucker_inst16.o", ["-DVT_TUCKER_NM=16"])]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMPILE_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 # the system host compiler; the image exports CXX/CC pointing at a wrapper nvcc cannot use
@@ -42,18 +45,20 @@ def build_lib(force=False, verbose=False, extra=()):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
-    sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    headers_t = max(os.path.getmtime(d) for d in _deps() if d.endswith(".h"))
+    sources = [s if isinstance(s, tuple) else (s, s[:-3] + ".o", []) for s in SOURCES]
+    sources = [s for s in sources if os.path.exists(os.path.join(CSRC, s[0]))]
+    headers_t = max(os.path.getmtime(d) for d in _deps() if d.endswith((".h", ".inl")))
 
-    def compile_one(src):
-        obj = os.path.join(OBJDIR, src[:-3] + ".o")
+    def compile_one(item):
+        src, objname, flags = item
+        obj = os.path.join(OBJDIR, objname)
         path = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), headers_t):
             return obj, ""
-        cmd = [nvcc()] + COMPILE_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + HOST_CXX + ["-c", path, "-o", obj]
+        cmd = [nvcc()] + COMPILE_FLAGS + list(flags) + list(extra) + (["-Xptxas", "-v"] if verbose else []) + HOST_CXX + ["-c", path, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+            raise RuntimeError(f"nvcc failed on {src} {flags}:\n{r.stdout}\n{r.stderr}")
         return obj, r.stdout + r.stderr
 
     with ThreadPoolExecutor(max_workers=min(len(sources), os.cpu_count() or 1)) as pool:

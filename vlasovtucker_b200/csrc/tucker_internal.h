@@ -68,6 +68,27 @@ struct TuckerParams {
     int* peerRout[kMaxPeers];
 };
 
+
+// ---- general kernel k_tucker: launch geometry shared by tucker.cu (host) and tucker_inst.cu (one instantiation each)
+constexpr int kThreads = 256;        // CTA size for velocity grids above 32 nodes per axis
+constexpr int kThreadsSmall = 128;   // ... and up to 32: more tets in flight per SM hide the eigen-solver's latency
+constexpr int kQB = 8;               // output rows per thread of a mode product
+__host__ __device__ constexpr int pad_ld(int n)   // smallest ld >= roundup(n, 8) with ld % 16 == 4
+{
+    const int p = (n + 7) / 8 * 8;
+    return p + ((4 - p % 16) + 16) % 16;
+}
+// doubles per staging tile buffer: the DFMA Gram / mode-product layouts or the zero-padded DMMA tiles
+__host__ __device__ constexpr int tile_cap(int nmax)
+{
+    const int a = ((nmax | 1) > (nmax + kQB - 1) / kQB * kQB ? (nmax | 1) : (nmax + kQB - 1) / kQB * kQB) * nmax;
+    const int b = pad_ld(nmax) * ((nmax + 7) / 8 * 8);
+    return a > b ? a : b;
+}
+void launch_k_tucker_16(int grid, size_t smem, cudaStream_t stream, const TuckerParams& P);
+void launch_k_tucker_32(int grid, size_t smem, cudaStream_t stream, const TuckerParams& P);
+void launch_k_tucker_64(int grid, size_t smem, cudaStream_t stream, const TuckerParams& P);
+
 // tucker_slab.cu: the slab-streaming step kernel (mode 0 only).  slab_eligible says whether it serves
 // this grid / rank cap / compression error; launch_tucker_slab runs one step of all owned tets.
 bool slab_eligible(const vt_ctx* ctx, const TuckerParams& P);
