@@ -232,7 +232,7 @@ int vt_tucker_get_factors(vt_ctx* ctx, int species, int tet, int32_t ranks[3], d
                           double* u1, double* u2);
 /* ParticleData<Tucker>::Density (src/particle_data.cpp:93-102); density may be NULL */
 int vt_tucker_density(vt_ctx* ctx, int species, double* density);
-/* which kernel the last vt_step_tucker of this species ran: 0 none yet, 1 general (csrc/tucker.cu, any grid up to
+/* which kernel the last vt_step_tucker of this species ran: 0 none yet, 1 general (csrc/tucker_kernel.inl, any grid up to
  * 64 nodes per axis, any compression error), 2 slab-streaming (csrc/tucker_slab.cu, 33..48 nodes per axis, rank cap
  * <= 16, comprErr >= 5.5e-7).  Diagnostics for bench.py and the tests; no reference counterpart. */
 int vt_tucker_last_kernel(vt_ctx* ctx, int species, int* kernel);

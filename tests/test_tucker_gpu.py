@@ -237,7 +237,7 @@ def test_errors(oracle_mod):
 def test_step_parity_small_compression_error(oracle_mod, eps):
     """comprErr below ~1e-7 (the class default is 1e-10, particle_data.h:49): singular values taken from
     Gram-matrix eigenvalues alone are noise below 1e-8 |sigma|; the device refines the trailing
-    eigen-directions inside their own subspace (csrc/tucker.cu, hosvd_truncate).  Against the oracle,
+    eigen-directions inside their own subspace (csrc/tucker_kernel.inl, hosvd_truncate).  Against the oracle,
     whose rounding uses a one-sided Jacobi SVD of the unfoldings as the reference uses Eigen's SVD."""
     m = oracle_mod.Mesh.load(mesh_path("fully_periodic_coarse.msh"), [(1, 2), (3, 4), (5, 6)])
     n, vmin, vmax = (9, 7, 5), [-3.0, -1.0, -1.0], [3.0, 1.0, 1.0]

@@ -9,19 +9,22 @@
 // the truncated HOSVD of the tensor the sum represents, with the reference's per-singular-value
 // rule (keep sigma_j > eps*|sigma|_2/sqrt(3), at least one, at most maxRank).  For the stacked ranks
 // of this update (R >= n almost immediately) the intermediate is a full n^3 tensor
-// anyway, so this first device implementation evaluates each sum densely in per-CTA scratch and
-// applies the same truncated HOSVD at the same six points per tet-step; the state between steps
-// stays compressed (core r^3 + three n x r factors per tet).  One CTA owns a tet from
-// reconstruction to the re-compressed result.
+// anyway, so the device evaluates each sum densely and applies the same truncated HOSVD at the same six
+// points per tet-step; the state between steps stays compressed (core r^3 + three n x r factors per tet).
 //
-//   reconstruct      core x1 U0 x2 U1 x3 U2                               (tucker.cpp:100-104)
-//   hosvd_truncate   per mode: Gram matrix of the unfolding, eigen-decomposition by one-sided
-//                    Jacobi with round-robin parallel ordering (one warp per column pair),
-//                    rank selection, then projection X x_k U_k^T          (tucker.cpp:34-50, 442-465)
-//
-// Accuracy note: singular values come from Gram matrices, so values below ~1e-8 sigma_1 are noise;
-// the rank rule is exact for compression errors >= ~1e-7 (the examples use 1e-6).  For the class
-// default 1e-10 the result is still a valid Tucker approximation within ~1e-8.
+// Files.  This one is the host side (state, dispatch, the ABI entry points).  Two kernels run a step:
+//   k_tucker_slab  tucker_slab.cu     slab-streaming, for grids of 33..48 nodes per axis, rank caps <= 16 and
+//                                     compression errors >= 5.5e-7 (see its header)
+//   k_tucker       tucker_kernel.inl  everything else, and the compress / reconstruct / |v.n| table modes of every
+//                                     species; compiled once per instantiation by tucker_inst.cu.  One CTA owns a tet
+//                                     from reconstruction to the re-compressed result, dense work arrays in a per-CTA
+//                                     global scratch:
+//     reconstruct      core x1 U0 x2 U1 x3 U2                                       (tucker.cpp:100-104)
+//     hosvd_truncate   Gram matrices of the three unfoldings (FP64 tensor cores up to 32 nodes per axis,
+//                      register-blocked DFMA above), three symmetric eigen-problems by three warps (Householder
+//                      tridiagonalisation + implicit QL), for eps < 5.5e-7 a two-level refinement of the trailing
+//                      eigen-directions inside their own subspace (Gram eigenvalues carry ~1e-16 of the trace as
+//                      noise), rank rule, projection X x_k U_k^T                    (tucker.cpp:34-50, 442-465)
 #include "tucker_internal.h"
 
 #include <algorithm>
