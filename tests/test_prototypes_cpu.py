@@ -27,3 +27,18 @@ def test_round_robin_jacobi_statement_matches_numpy(capsys):
     mod = _load("jacobi_round_robin")
     mod.main(sizes=(17, 12))
     assert capsys.readouterr().out.rstrip().endswith("ok")
+
+
+def test_single_reduction_cg_reaches_the_reference_stopping_rule(capsys):
+    """scripts/prototypes/cg_single_reduction.py: the Chronopoulos-Gear form of PCG (one global reduction per iteration,
+    the planned next step of csrc/poisson.cu) meets Eigen's |r| <= eps |b| on the oracle's Poisson matrix in as many
+    iterations as the classic form and gives the same solution."""
+    mod = _load("cg_single_reduction")
+    mod.main(6)
+    out = capsys.readouterr().out.splitlines()
+    it_classic = int(out[1].split("iterations")[1].split()[0])
+    one = out[2]
+    it_one = int(one.split("iterations")[1].split()[0])
+    dx = float(one.split("|x - x_classic| / |x|")[1])
+    assert "not converged" not in one
+    assert abs(it_one - it_classic) <= 3 and dx <= 1e-11
