@@ -145,6 +145,7 @@ __host__ __device__ inline SlabLay slab_layout(const int n[3], int rK)
     }
     o = o > passEnd ? o : passEnd;
     if (o < L.oV[0] + 4 * L.slab) o = L.oV[0] + 4 * L.slab;   // pass 2 keeps its four slab buffers behind G0, G1, G2
+    if (o < rK * rK * L.p[1]) o = rK * rK * L.p[1];           // pass 3 collects W (rK x p1 x rK) at the bottom of the region
     for (int k = 0; k < 3; k++) {
         L.oUnew[k] = o;
         o += L.LU[k] * rK;
